@@ -1,0 +1,324 @@
+// Per-tile alpha blending: CUDA stages "70 render" (+81-83 statistics) and "b10 render"
+// (/root/reference/analyze_statistic.py:1981-1987) -- the second half of
+// GaussianRasterizer.render_gaussians and its autograd backward
+// (/root/reference/gaussian_renderer/__init__.py:1271-1282, train_internal.py:195).
+//
+// One CTA = one 16x16 tile (BLOCK_X/Y are observable through _C.get_block_XY and baked into the
+// reference's strip arithmetic, loss_distribution.py:2321-2330).  Each warp owns an 8x4 pixel
+// block so that warp votes can skip splats that miss the block.  Sorted splat ids are turned
+// into 48-byte packed records (3 x float4, built by k_count_tiles) staged in shared memory.
+//
+// Both kernels are bound by fp32 ALU / MUFU work over (pixel, splat) pairs, not by HBM: the
+// algorithmic traffic is 40 B per instance forward and 76 B backward against
+// 256 pair evaluations per instance.
+//
+// Backward reduction hierarchy (replaces the 9 global atomics per pixel per splat of the
+// classical design): lane -> warp by a 9-value transposing butterfly (14 shuffles instead of 45)
+// -> per-warp private shared-memory slots (no shared atomics: sm_100 has no native fp32 ATOMS.ADD)
+// -> one thread per splat sums the warps and issues ONE set of 9 global RED.ADD per (splat, tile).
+#include "common.cuh"
+
+#define BL_THREADS 256
+#define FW_CHUNK 256
+#define BW_CHUNK 128
+#define BW_WARPS (BL_THREADS / 32)
+#define BW_STRIDE (BW_CHUNK + 1)
+
+#define ALPHA_MIN (1.0f / 255.0f)
+#define ALPHA_MAX 0.99f
+#define T_EPS 0.0001f
+// splats whose power is this far below ln(1/(255*opacity)) cannot reach alpha >= 1/255: skip exp()
+#define THR_MARGIN 0.02f
+
+GS_D float gs_alpha_of(float opacity, float power, float &G) {
+    G = __expf(power);
+    return fminf(ALPHA_MAX, opacity * G);
+}
+
+GS_D void pixel_of_thread(int tile, int gx, int &px, int &py) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    px = (tile % gx) * GS_BLOCK_X + (w & 1) * 8 + (lane & 7);
+    py = (tile / gx) * GS_BLOCK_Y + (w >> 1) * 4 + (lane >> 3);
+}
+
+__global__ void __launch_bounds__(BL_THREADS)
+k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restrict__ bg,
+            const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
+            const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
+            uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats) {
+    __shared__ float4 s_r0[FW_CHUNK], s_r1[FW_CHUNK], s_r2[FW_CHUNK];
+    __shared__ unsigned long long s_stats[3];
+    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
+    const int tile = blockIdx.x;
+    int px, py;
+    pixel_of_thread(tile, gx, px, py);
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)py * W + px;
+    if (!compute_locally[tile]) {  // non-local tiles must read exactly 0 (loss_distribution.py:1875)
+        if (inside) { image[pix] = 0.f; image[HW + pix] = 0.f; image[2 * HW + pix] = 0.f; }
+        return;
+    }
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+    const float pxf = (float)px, pyf = (float)py;
+    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t last = 0, blended = 0, considered = 0;
+    bool done = !inside;
+    for (int base = 0; base < total; base += FW_CHUNK) {
+        if (__syncthreads_count(done) == BL_THREADS) break;
+        const int cnt = min(FW_CHUNK, total - base);
+        if ((int)threadIdx.x < cnt) {
+            const uint32_t g = ids[range.x + base + threadIdx.x];
+            const float4 *r = rec + (size_t)3 * g;
+            s_r0[threadIdx.x] = __ldg(r); s_r1[threadIdx.x] = __ldg(r + 1); s_r2[threadIdx.x] = __ldg(r + 2);
+        }
+        __syncthreads();
+        if (__all_sync(0xffffffffu, done)) continue;
+        for (int j = 0; j < cnt; j++) {
+            const float4 a = s_r0[j], b = s_r1[j];
+            const float dx = a.x - pxf, dy = a.y - pyf;
+            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+            bool ok = !done && power <= 0.f && power >= b.z - THR_MARGIN;
+            if (!__any_sync(0xffffffffu, ok)) continue;
+            if (ok) {
+                float G;
+                const float alpha = gs_alpha_of(b.y, power, G);
+                if (alpha >= ALPHA_MIN) {
+                    const float test_T = T * (1.f - alpha);
+                    if (test_T < T_EPS) {
+                        done = true;
+                        considered = (uint32_t)(base + j + 1);
+                    } else {
+                        const float4 c = s_r2[j];
+                        const float w = alpha * T;
+                        C0 += b.w * w; C1 += c.x * w; C2 += c.y * w;
+                        T = test_T;
+                        last = (uint32_t)(base + j + 1);
+                        blended++;
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;  // reached by the whole warp (uniform vote above)
+        }
+    }
+    if (inside) {
+        image[pix] = C0 + T * bg[0];
+        image[HW + pix] = C1 + T * bg[1];
+        image[2 * HW + pix] = C2 + T * bg[2];
+        final_T[pix] = T;
+        n_contrib[pix] = last;
+        if (considered == 0) considered = (uint32_t)total;
+    }
+    if (stats) {  // stages 81-83: sums of tile-list length / entries walked / entries blended
+        if (threadIdx.x < 3) s_stats[threadIdx.x] = 0ull;
+        __syncthreads();
+        unsigned long long v0 = inside ? (unsigned long long)total : 0ull, v1 = inside ? considered : 0u,
+                           v2 = inside ? blended : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_stats[0], v0); atomicAdd(&s_stats[1], v1); atomicAdd(&s_stats[2], v2);
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) atomicAdd(&stats[threadIdx.x], s_stats[threadIdx.x]);
+    }
+}
+
+// 9-value warp reduction.  After the call every lane holds in v[0] the warp total of value
+// (lane >> 2) & 7, and in v[8] the warp total of value 8.
+GS_D void warp_reduce9(float v[9], int lane) {
+    {
+        const bool h = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float send = h ? v[i] : v[i + 4], keep = h ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool h = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float send = h ? v[i] : v[i + 2], keep = h ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool h = lane & 4;
+        const float send = h ? v[0] : v[1], keep = h ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[8] += __shfl_xor_sync(0xffffffffu, v[8], o);
+}
+
+__global__ void __launch_bounds__(BL_THREADS)
+k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restrict__ bg,
+            const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
+            const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
+            const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
+            float *__restrict__ d_means2D, float *__restrict__ d_conic_opacity, float *__restrict__ d_rgb) {
+    __shared__ float4 s_r0[BW_CHUNK], s_r1[BW_CHUNK], s_r2[BW_CHUNK];
+    __shared__ uint32_t s_id[BW_CHUNK];
+    __shared__ float s_acc[BW_WARPS][9][BW_STRIDE];
+    __shared__ uint32_t s_mask[BW_WARPS][BW_CHUNK / 32];
+    __shared__ uint32_t s_max[BW_WARPS];
+    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
+    const int tile = blockIdx.x;
+    if (!compute_locally[tile]) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int px, py;
+    pixel_of_thread(tile, gx, px, py);
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)py * W + px;
+    const uint2 range = ranges[tile];
+    const float pxf = (float)px, pyf = (float)py;
+    const float T_final = inside ? final_T[pix] : 0.f;
+    const uint32_t last = inside ? n_contrib[pix] : 0u;
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+    if (inside) { dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix]; }
+    const float bgdot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
+    const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
+    // entries past the tile's deepest last-contributor cannot matter
+    uint32_t m = last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_max[warp] = m;
+    __syncthreads();
+    uint32_t n_total = 0;
+#pragma unroll
+    for (int w = 0; w < BW_WARPS; w++) n_total = max(n_total, s_max[w]);
+    float T = T_final, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
+    const int n_chunks = ((int)n_total + BW_CHUNK - 1) / BW_CHUNK;
+    for (int c = n_chunks - 1; c >= 0; c--) {
+        const int base = c * BW_CHUNK;
+        const int cnt = min(BW_CHUNK, (int)n_total - base);
+        __syncthreads();  // previous chunk's flush has finished reading shared memory
+        if ((int)threadIdx.x < cnt) {
+            const uint32_t g = ids[range.x + base + threadIdx.x];
+            s_id[threadIdx.x] = g;
+            const float4 *r = rec + (size_t)3 * g;
+            s_r0[threadIdx.x] = __ldg(r); s_r1[threadIdx.x] = __ldg(r + 1); s_r2[threadIdx.x] = __ldg(r + 2);
+        }
+        uint32_t wmask = 0u;  // lane q holds bits [32q, 32q+32) of "this warp produced a partial for entry j"
+        __syncthreads();
+        for (int j = cnt - 1; j >= 0; j--) {
+            const float4 a = s_r0[j], b = s_r1[j];
+            const float dx = a.x - pxf, dy = a.y - pyf;
+            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+            bool ok = ((uint32_t)(base + j) < last) && power <= 0.f && power >= b.z - THR_MARGIN;
+            if (!__any_sync(0xffffffffu, ok)) continue;
+            float G;
+            const float alpha = gs_alpha_of(b.y, power, G);
+            ok = ok && alpha >= ALPHA_MIN;
+            if (!__any_sync(0xffffffffu, ok)) continue;
+            float v[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) v[q] = 0.f;
+            if (ok) {
+                const float4 cc = s_r2[j];
+                const float col0 = b.w, col1 = cc.x, col2 = cc.y;
+                T = T / (1.f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                lc0 = col0; lc1 = col1; lc2 = col2;
+                float dL_dalpha = (col0 - acc0) * dp0 + (col1 - acc1) * dp1 + (col2 - acc2) * dp2;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
+                const float dL_dG = b.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * a.z - gdy * a.w;
+                const float dG_ddely = -gdy * b.x - gdx * a.w;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[2] = -0.5f * gdx * dx * dL_dG;
+                v[3] = -gdx * dy * dL_dG;
+                v[4] = -0.5f * gdy * dy * dL_dG;
+                v[5] = G * dL_dalpha;
+                v[6] = dchannel_dcolor * dp0;
+                v[7] = dchannel_dcolor * dp1;
+                v[8] = dchannel_dcolor * dp2;
+            }
+            warp_reduce9(v, lane);
+            if ((lane & 3) == 0) s_acc[warp][lane >> 2][j] = v[0];
+            if (lane == 1) s_acc[warp][8][j] = v[8];
+            if (lane == (j >> 5)) wmask |= 1u << (j & 31);
+        }
+        if (lane < BW_CHUNK / 32) s_mask[warp][lane] = wmask;
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            const int j = threadIdx.x;
+            float s[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) s[q] = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < BW_WARPS; w++) {
+                if ((s_mask[w][j >> 5] >> (j & 31)) & 1u) {
+                    any = true;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) s[q] += s_acc[w][q][j];
+                }
+            }
+            if (any) {
+                const uint32_t g = s_id[j];
+                atomicAdd(d_means2D + 2 * (size_t)g, s[0]);
+                atomicAdd(d_means2D + 2 * (size_t)g + 1, s[1]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g, s[2]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 1, s[3]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 2, s[4]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 3, s[5]);
+                atomicAdd(d_rgb + 3 * (size_t)g, s[6]);
+                atomicAdd(d_rgb + 3 * (size_t)g + 1, s[7]);
+                atomicAdd(d_rgb + 3 * (size_t)g + 2, s[8]);
+            }
+        }
+    }
+}
+
+int gs_launch_blend_forward(int64_t R, int H, int W, const float *rec, const float *bg, const uint8_t *compute_locally,
+                            const uint32_t *ranges, const uint32_t *ids_sorted, float *image, float *final_T,
+                            uint32_t *n_contrib, int64_t *stats, cudaStream_t stream) {
+    (void)R;
+    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
+    if (stats) GS_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t), stream));
+    k_blend_fwd<<<gx * gy, BL_THREADS, 0, stream>>>(W, H, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
+                                                    reinterpret_cast<const uint2 *>(ranges), ids_sorted, image, final_T,
+                                                    n_contrib, reinterpret_cast<unsigned long long *>(stats));
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_render_backward(int P, int64_t R, int image_height, int image_width, const float *rec,
+                                  const float *bg, const uint8_t *compute_locally, const uint32_t *ranges,
+                                  const uint32_t *ids_sorted, const float *final_T, const uint32_t *n_contrib,
+                                  const float *dL_dimage, float *dL_dmeans2D, float *dL_dconic_opacity, float *dL_drgb,
+                                  void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GS_REQUIRE(P >= 0 && R >= 0 && image_height > 0 && image_width > 0, "sizes");
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(dL_dmeans2D && dL_dconic_opacity && dL_drgb, "null output");
+    GS_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 2 * (size_t)P, stream));
+    GS_CUDA_TRY(cudaMemsetAsync(dL_dconic_opacity, 0, sizeof(float) * 4 * (size_t)P, stream));
+    GS_CUDA_TRY(cudaMemsetAsync(dL_drgb, 0, sizeof(float) * 3 * (size_t)P, stream));
+    if (R == 0) return GS_OK;
+    GS_REQUIRE(rec && bg && compute_locally && ranges && ids_sorted && final_T && n_contrib && dL_dimage, "null input");
+    const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
+    k_blend_bwd<<<gx * gy, BL_THREADS, 0, stream>>>(image_width, image_height, reinterpret_cast<const float4 *>(rec), bg,
+                                                    compute_locally, reinterpret_cast<const uint2 *>(ranges), ids_sorted,
+                                                    final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity,
+                                                    dL_drgb);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

@@ -1,0 +1,215 @@
+// Fused per-strip L1 + SSIM loss, forward and backward.
+// Replaces the ~20 torch kernels (5 depthwise 11x11 F.conv2d + elementwise) of
+// /root/reference/gaussian_renderer/loss_distribution.py:2536-2585 with utils/loss_utils.py:88-132:
+//   Ll1  = sum |x - y|      / (3 H W)          (pixelwise_l1_with_mask, mask == all ones in the live path)
+//   ssim = sum ssim_map(x,y) / (3 H W)          (11x11 Gaussian window sigma 1.5, ZERO padding at the strip
+//                                               edges -- the live path exchanges no halo)
+// with x = rendered strip rows [row0,row1) of the full (3,H,W) image, y = clamp(gt_u8/255, 0, 1).
+// The window is applied separably (row pass then column pass) from shared memory.
+//
+// HBM bound: forward reads 15 B and writes 36 B per pixel-channel triple (three derivative maps kept for
+// the backward), backward reads 51 B and writes 12 B; no tensor-core shaped work.
+#include "common.cuh"
+
+#define LS_TILE 32
+#define LS_HALO 5
+#define LS_IN (LS_TILE + 2 * LS_HALO)
+#define LS_THREADS 256
+
+__device__ __constant__ float c_gauss[11];
+static bool g_gauss_ready = false;
+
+static int ensure_gauss() {
+    if (g_gauss_ready) return GS_OK;
+    // utils/loss_utils.py:26-34: fp32 exp values normalised in fp32
+    float g[11], s = 0.f;
+    for (int k = 0; k < 11; k++) { g[k] = (float)exp(-((double)(k - 5) * (k - 5)) / (2.0 * 1.5 * 1.5)); s += g[k]; }
+    for (int k = 0; k < 11; k++) g[k] = g[k] / s;
+    GS_CUDA_TRY(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
+    g_gauss_ready = true;
+    return GS_OK;
+}
+
+extern "C" size_t gs_loss_temp_bytes(int rows, int image_width) {
+    return (size_t)9 * (size_t)(rows > 0 ? rows : 0) * (size_t)image_width * sizeof(float) + 256;
+}
+
+// temp layout: [0,16) two double accumulators; [256, ...) maps (3 maps x 3 channels x rows x W)
+__global__ void __launch_bounds__(LS_THREADS)
+k_loss_fwd(int W, int H, int row0, int rows, const float *__restrict__ image, const uint8_t *__restrict__ gt,
+           float *__restrict__ maps, double *__restrict__ sums) {
+    __shared__ float s_x[LS_IN][LS_IN + 1], s_y[LS_IN][LS_IN + 1];
+    __shared__ float s_h[5][LS_IN][LS_TILE + 1];
+    __shared__ float s_red[2][LS_THREADS / 32];
+    const int tx0 = blockIdx.x * LS_TILE, ty0 = blockIdx.y * LS_TILE;  // strip-local tile origin
+    const size_t HW = (size_t)H * W, SW = (size_t)rows * W;
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    float l1 = 0.f, ss = 0.f;
+    for (int ch = 0; ch < 3; ch++) {
+        for (int k = threadIdx.x; k < LS_IN * LS_IN; k += LS_THREADS) {
+            const int r = k / LS_IN, c = k % LS_IN;
+            const int y = ty0 + r - LS_HALO, x = tx0 + c - LS_HALO;
+            float vx = 0.f, vy = 0.f;
+            if (y >= 0 && y < rows && x >= 0 && x < W) {
+                vx = image[ch * HW + (size_t)(row0 + y) * W + x];
+                vy = fminf(1.f, fmaxf(0.f, (float)gt[ch * SW + (size_t)y * W + x] / 255.0f));
+            }
+            s_x[r][c] = vx; s_y[r][c] = vy;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < LS_IN * LS_TILE; k += LS_THREADS) {
+            const int r = k / LS_TILE, c = k % LS_TILE;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 11; t++) {
+                const float g = c_gauss[t], vx = s_x[r][c + t], vy = s_y[r][c + t];
+                a0 += g * vx; a1 += g * vy; a2 += g * vx * vx; a3 += g * vy * vy; a4 += g * vx * vy;
+            }
+            s_h[0][r][c] = a0; s_h[1][r][c] = a1; s_h[2][r][c] = a2; s_h[3][r][c] = a3; s_h[4][r][c] = a4;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < LS_TILE * LS_TILE; k += LS_THREADS) {
+            const int r = k / LS_TILE, c = k % LS_TILE;
+            const int y = ty0 + r, x = tx0 + c;
+            if (y < rows && x < W) {
+                float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 11; t++) {
+                    const float g = c_gauss[t];
+                    m1 += g * s_h[0][r + t][c]; m2 += g * s_h[1][r + t][c]; e11 += g * s_h[2][r + t][c];
+                    e22 += g * s_h[3][r + t][c]; e12 += g * s_h[4][r + t][c];
+                }
+                const float s1 = e11 - m1 * m1, s2 = e22 - m2 * m2, s12 = e12 - m1 * m2;
+                const float A = 2.f * m1 * m2 + C1, B = 2.f * s12 + C2, Cc = m1 * m1 + m2 * m2 + C1, D = s1 + s2 + C2;
+                const float iCD = 1.f / (Cc * D);
+                ss += A * B * iCD;
+                const float vx = s_x[r + LS_HALO][c + LS_HALO], vy = s_y[r + LS_HALO][c + LS_HALO];
+                l1 += fabsf(vx - vy);
+                // d map / d(mu1), d(E[x^2]), d(E[xy])
+                const float dm1 = 2.f * m2 * (B - A) * iCD - 2.f * m1 * A * B * (D - Cc) * iCD * iCD;
+                const float d11 = -A * B * iCD / D;
+                const float d12 = 2.f * A * iCD;
+                const size_t o = (size_t)ch * SW + (size_t)y * W + x;
+                maps[o] = dm1; maps[3 * SW + o] = d11; maps[6 * SW + o] = d12;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { l1 += __shfl_xor_sync(0xffffffffu, l1, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = l1; s_red[1][threadIdx.x >> 5] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < LS_THREADS / 32; w++) { a += (double)s_red[0][w]; b += (double)s_red[1][w]; }
+        atomicAdd(&sums[0], a); atomicAdd(&sums[1], b);
+    }
+}
+
+__global__ void k_loss_finalize(const double *__restrict__ sums, double inv_norm, float *__restrict__ out) {
+    out[0] = (float)(sums[0] * inv_norm);
+    out[1] = (float)(sums[1] * inv_norm);
+}
+
+__global__ void __launch_bounds__(LS_THREADS)
+k_loss_bwd(int W, int H, int row0, int rows, const float *__restrict__ image, const uint8_t *__restrict__ gt,
+           const float *__restrict__ maps, const float *__restrict__ grad_l1, const float *__restrict__ grad_ssim,
+           float inv_norm, float *__restrict__ dimg) {
+    __shared__ float s_m[3][LS_IN][LS_IN + 1];
+    __shared__ float s_h[3][LS_IN][LS_TILE + 1];
+    const int tx0 = blockIdx.x * LS_TILE, ty0 = blockIdx.y * LS_TILE;
+    const size_t HW = (size_t)H * W, SW = (size_t)rows * W;
+    const float gl1 = grad_l1[0] * inv_norm, gss = grad_ssim[0] * inv_norm;
+    for (int ch = 0; ch < 3; ch++) {
+        for (int k = threadIdx.x; k < LS_IN * LS_IN; k += LS_THREADS) {
+            const int r = k / LS_IN, c = k % LS_IN;
+            const int y = ty0 + r - LS_HALO, x = tx0 + c - LS_HALO;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            if (y >= 0 && y < rows && x >= 0 && x < W) {
+                const size_t o = (size_t)ch * SW + (size_t)y * W + x;
+                v0 = maps[o]; v1 = maps[3 * SW + o]; v2 = maps[6 * SW + o];
+            }
+            s_m[0][r][c] = v0; s_m[1][r][c] = v1; s_m[2][r][c] = v2;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < LS_IN * LS_TILE; k += LS_THREADS) {
+            const int r = k / LS_TILE, c = k % LS_TILE;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 11; t++) {
+                const float g = c_gauss[t];
+                a0 += g * s_m[0][r][c + t]; a1 += g * s_m[1][r][c + t]; a2 += g * s_m[2][r][c + t];
+            }
+            s_h[0][r][c] = a0; s_h[1][r][c] = a1; s_h[2][r][c] = a2;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < LS_TILE * LS_TILE; k += LS_THREADS) {
+            const int r = k / LS_TILE, c = k % LS_TILE;
+            const int y = ty0 + r, x = tx0 + c;
+            if (y < rows && x < W) {
+                float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 11; t++) {
+                    const float g = c_gauss[t];
+                    b0 += g * s_h[0][r + t][c]; b1 += g * s_h[1][r + t][c]; b2 += g * s_h[2][r + t][c];
+                }
+                const size_t oi = ch * HW + (size_t)(row0 + y) * W + x;
+                const float vx = image[oi];
+                const float vy = fminf(1.f, fmaxf(0.f, (float)gt[ch * SW + (size_t)y * W + x] / 255.0f));
+                const float d = vx - vy;
+                const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+                dimg[oi] = gl1 * sgn + gss * (b0 + 2.f * vx * b1 + vy * b2);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int gs_loss_forward(int image_height, int image_width, int row0, int row1, const float *image,
+                               const uint8_t *gt_u8, float *out_l1_ssim, void *temp, size_t temp_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int rows = row1 - row0;
+    GS_REQUIRE(image_height > 0 && image_width > 0 && row0 >= 0 && row1 <= image_height && rows > 0, "strip rows");
+    GS_REQUIRE(image && gt_u8 && out_l1_ssim && temp, "null pointer");
+    if (temp_bytes < gs_loss_temp_bytes(rows, image_width)) {
+        gs_set_error("gs_loss_forward: temp too small");
+        return GS_ENOMEM;
+    }
+    int rc = ensure_gauss();
+    if (rc != GS_OK) return rc;
+    double *sums = (double *)temp;
+    float *maps = (float *)((char *)temp + 256);
+    GS_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), stream));
+    dim3 grid((image_width + LS_TILE - 1) / LS_TILE, (rows + LS_TILE - 1) / LS_TILE);
+    k_loss_fwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, image, gt_u8, maps, sums);
+    GS_LAUNCH_CHECK();
+    k_loss_finalize<<<1, 1, 0, stream>>>(sums, 1.0 / (3.0 * (double)image_height * (double)image_width), out_l1_ssim);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_loss_backward(int image_height, int image_width, int row0, int row1, const float *image,
+                                const uint8_t *gt_u8, const void *temp, const float *grad_l1, const float *grad_ssim,
+                                float *dL_dimage, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int rows = row1 - row0;
+    GS_REQUIRE(image_height > 0 && image_width > 0 && row0 >= 0 && row1 <= image_height && rows > 0, "strip rows");
+    GS_REQUIRE(image && gt_u8 && temp && grad_l1 && grad_ssim && dL_dimage, "null pointer");
+    int rc = ensure_gauss();
+    if (rc != GS_OK) return rc;
+    const float *maps = (const float *)((const char *)temp + 256);
+    const size_t HW = (size_t)image_height * image_width;
+    // rows outside the strip carry no loss
+    for (int ch = 0; ch < 3; ch++) {
+        if (row0 > 0) GS_CUDA_TRY(cudaMemsetAsync(dL_dimage + ch * HW, 0, sizeof(float) * (size_t)row0 * image_width, stream));
+        if (row1 < image_height)
+            GS_CUDA_TRY(cudaMemsetAsync(dL_dimage + ch * HW + (size_t)row1 * image_width, 0,
+                                        sizeof(float) * (size_t)(image_height - row1) * image_width, stream));
+    }
+    dim3 grid((image_width + LS_TILE - 1) / LS_TILE, (rows + LS_TILE - 1) / LS_TILE);
+    k_loss_bwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, image, gt_u8, maps, grad_l1,
+                                                grad_ssim, (float)(1.0 / (3.0 * (double)image_height * (double)image_width)),
+                                                dL_dimage);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

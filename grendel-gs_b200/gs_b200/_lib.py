@@ -1,0 +1,82 @@
+"""ctypes binding of the C-ABI library (include/grendel_gs_b200.h).
+
+This is the "reference-side stub" of INTEGRATION.md: plain pointers and sizes go in, torch only
+supplies device memory and the current CUDA stream.  There is NO fallback: if the shared library is
+missing or a call fails, an exception is raised (the product path never routes through oracle/ or
+any CPU implementation).
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "lib", "libgrendel_gs_b200.so")
+
+_vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/grendel_gs_b200.h declaration by declaration
+SIGNATURES = {
+    "gs_last_error": (C.c_char_p, []),
+    "gs_version": (C.c_char_p, []),
+    "gs_get_block_xy": (_i, [C.POINTER(_i)] * 3),
+    "gs_preprocess_forward": (_i, [_i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_preprocess_backward": (_i, [_i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_get_local2j_ids_bool": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gs_get_local2j_ids_bool_rects": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gs_render_count_temp_bytes": (_sz, [_i]),
+    "gs_render_count": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
+    "gs_render_sort_temp_bytes": (_sz, [_i64]),
+    "gs_render_forward": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                               _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_render_backward": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_loss_temp_bytes": (_sz, [_i, _i]),
+    "gs_loss_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gs_loss_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_mask_scan_temp_bytes": (_sz, [_i]),
+    "gs_mask_scan": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gs_pack_rows": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_unpack_rows": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+class GsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; raises ImportError (loudly) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this operator.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise GsError with gs_last_error() on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise GsError(f"{name} failed (code {rc}): {lib.gs_last_error().decode(errors='replace')}")
+
+
+def query(name, *args):
+    return getattr(load(), name)(*args)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,322 @@
+"""Autograd operators over the C ABI: the host-side mirror of the reference's
+`diff_gaussian_rasterization` wrappers.
+
+  preprocess_gaussians  /root/reference/gaussian_renderer/__init__.py:949-958
+  render_gaussians      /root/reference/gaussian_renderer/__init__.py:1271-1282
+  get_local2j_ids_bool  /root/reference/gaussian_renderer/workload_division.py:721-744
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+
+BLOCK_X, BLOCK_Y, ONE_DIM_BLOCK_SIZE = 16, 16, 256
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (this operator has no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+class LazyMs:
+    """Elapsed milliseconds between two CUDA events, resolved on first numeric use.
+
+    cuda_args["stats_collector"]["forward_render_time"/"backward_render_time"] must be readable as
+    numbers by finish_strategy_final (/root/reference/gaussian_renderer/workload_division.py:953-957).
+    Resolving lazily removes two host syncs per camera from the step; set GS_B200_EAGER_TIMING=1 to
+    store plain floats instead."""
+
+    __slots__ = ("_s", "_e", "_v")
+
+    def __init__(self, start, end):
+        self._s, self._e, self._v = start, end, None
+
+    def value(self):
+        if self._v is None:
+            self._e.synchronize()
+            self._v = float(self._s.elapsed_time(self._e))
+            self._s = self._e = None
+        return self._v
+
+    def __float__(self):
+        return self.value()
+
+    def __add__(self, o):
+        return self.value() + float(o)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self.value() - float(o)
+
+    def __rsub__(self, o):
+        return float(o) - self.value()
+
+    def __mul__(self, o):
+        return self.value() * float(o)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return self.value() / float(o)
+
+    def __rtruediv__(self, o):
+        return float(o) / self.value()
+
+    def __lt__(self, o):
+        return self.value() < float(o)
+
+    def __gt__(self, o):
+        return self.value() > float(o)
+
+    def __repr__(self):
+        return repr(self.value())
+
+    def __format__(self, spec):
+        return format(self.value(), spec)
+
+
+def _timed(collector, key, start, end):
+    if collector is None:
+        return
+    v = LazyMs(start, end)
+    collector[key] = v.value() if os.environ.get("GS_B200_EAGER_TIMING") == "1" else v
+
+
+class _PreprocessGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, scales, rotations, shs, opacities, rs):
+        means3D, scales, rotations = _f32c(means3D, "means3D"), _f32c(scales, "scales"), _f32c(rotations, "rotations")
+        shs, opacities = _f32c(shs, "shs"), _f32c(opacities, "opacities")
+        P = means3D.shape[0]
+        if shs.dim() != 3 or shs.shape[1] != 16 or shs.shape[2] != 3:
+            raise ValueError(f"shs must be (P,16,3) (scene/gaussian_model.py:122-125), got {tuple(shs.shape)}")
+        if tuple(means3D.shape) != (P, 3) or tuple(scales.shape) != (P, 3) or tuple(rotations.shape) != (P, 4) \
+                or opacities.numel() != P or shs.shape[0] != P:
+            raise ValueError("inconsistent Gaussian parameter shapes")
+        dev = means3D.device
+        vm, pm, cp = _f32c(rs.viewmatrix, "viewmatrix"), _f32c(rs.projmatrix, "projmatrix"), _f32c(rs.campos, "campos")
+        means2D = torch.empty((P, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((P,), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        conic_opacity = torch.empty((P, 4), dtype=torch.float32, device=dev)
+        rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        clamped = torch.empty((P,), dtype=torch.uint8, device=dev)
+        _lib.call("gs_preprocess_forward", P, int(rs.sh_degree), means3D.data_ptr(), scales.data_ptr(),
+                  float(rs.scale_modifier), rotations.data_ptr(), opacities.data_ptr(), shs.data_ptr(), vm.data_ptr(),
+                  pm.data_ptr(), cp.data_ptr(), int(rs.image_width), int(rs.image_height), float(rs.tanfovx),
+                  float(rs.tanfovy), means2D.data_ptr(), depths.data_ptr(), radii.data_ptr(), conic_opacity.data_ptr(),
+                  rgb.data_ptr(), clamped.data_ptr(), _stream())
+        ctx.rs = rs
+        ctx.cam = (vm, pm, cp)
+        ctx.save_for_backward(means3D, scales, rotations, shs, radii, clamped)
+        ctx.mark_non_differentiable(radii, depths)
+        return means2D, rgb, conic_opacity, radii, depths
+
+    @staticmethod
+    def backward(ctx, g_means2D, g_rgb, g_conic_opacity, _g_radii, _g_depths):
+        means3D, scales, rotations, shs, radii, clamped = ctx.saved_tensors
+        rs = ctx.rs
+        vm, pm, cp = ctx.cam
+        P = means3D.shape[0]
+        dev = means3D.device
+
+        def z(g, shape):
+            return torch.zeros(shape, dtype=torch.float32, device=dev) if g is None else _f32c(g, "grad")
+
+        g_means2D, g_rgb, g_conic_opacity = z(g_means2D, (P, 2)), z(g_rgb, (P, 3)), z(g_conic_opacity, (P, 4))
+        d_means3D = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        d_scales = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        d_rot = torch.empty((P, 4), dtype=torch.float32, device=dev)
+        d_opac = torch.empty((P, 1), dtype=torch.float32, device=dev)
+        d_shs = torch.empty((P, 16, 3), dtype=torch.float32, device=dev)
+        _lib.call("gs_preprocess_backward", P, int(rs.sh_degree), means3D.data_ptr(), scales.data_ptr(),
+                  float(rs.scale_modifier), rotations.data_ptr(), shs.data_ptr(), vm.data_ptr(), pm.data_ptr(),
+                  cp.data_ptr(), int(rs.image_width), int(rs.image_height), float(rs.tanfovx), float(rs.tanfovy),
+                  radii.data_ptr(), clamped.data_ptr(), g_means2D.data_ptr(), g_conic_opacity.data_ptr(),
+                  g_rgb.data_ptr(), d_means3D.data_ptr(), d_scales.data_ptr(), d_rot.data_ptr(), d_opac.data_ptr(),
+                  d_shs.data_ptr(), _stream())
+        return d_means3D, d_scales, d_rot, d_shs, d_opac, None
+
+
+def preprocess_gaussians(means3D, scales, rotations, shs, opacities, raster_settings, cuda_args=None):
+    """-> (means2D (P,2) pixels, rgb (P,3), conic_opacity (P,4), radii (P) int32, depths (P))."""
+    return _PreprocessGaussians.apply(means3D, scales, rotations, shs, opacities, raster_settings)
+
+
+def _tiles(rs):
+    return (int(rs.image_height) + BLOCK_Y - 1) // BLOCK_Y, (int(rs.image_width) + BLOCK_X - 1) // BLOCK_X
+
+
+class _RenderGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2D, conic_opacity, rgb, depths, radii, compute_locally, rs, collector):
+        means2D, conic_opacity, rgb = _f32c(means2D, "means2D"), _f32c(conic_opacity, "conic_opacity"), _f32c(rgb, "rgb")
+        depths = _f32c(depths, "depths")
+        if radii.dtype != torch.int32:
+            radii = radii.to(torch.int32)
+        radii = radii.contiguous()
+        P = means2D.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        ty, tx = _tiles(rs)
+        T = ty * tx
+        dev = means2D.device
+        if compute_locally is None:
+            cl = torch.ones((T,), dtype=torch.uint8, device=dev)
+        else:
+            if compute_locally.numel() != T:
+                raise ValueError(f"compute_locally must have {ty}x{tx} entries, got {tuple(compute_locally.shape)}")
+            cl = compute_locally.contiguous()
+            cl = cl.view(torch.uint8) if cl.dtype == torch.bool else cl.to(torch.uint8)
+        bg = _f32c(rs.bg, "bg")
+        s = _stream()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        offsets = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
+        rec = torch.empty((max(P, 1), 12), dtype=torch.float32, device=dev)
+        tb = _lib.query("gs_render_count_temp_bytes", P)
+        temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
+        R = C.c_int64(0)
+        _lib.call("gs_render_count", P, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
+                  radii.data_ptr(), cl.data_ptr(), offsets.data_ptr(), rec.data_ptr(), temp.data_ptr(), tb,
+                  C.byref(R), s)
+        R = int(R.value)
+        Ra = max(R, 1)
+        keys = torch.empty((2, Ra), dtype=torch.int64, device=dev)
+        ids = torch.empty((2, Ra), dtype=torch.int32, device=dev)
+        sb = _lib.query("gs_render_sort_temp_bytes", R)
+        sort_temp = torch.empty((sb,), dtype=torch.uint8, device=dev)
+        ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
+        image = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        final_T = torch.empty((H, W), dtype=torch.float32, device=dev)
+        n_contrib = torch.empty((H, W), dtype=torch.int32, device=dev)
+        stats = torch.empty((3,), dtype=torch.int64, device=dev)
+        _lib.call("gs_render_forward", P, R, H, W, means2D.data_ptr(), depths.data_ptr(), radii.data_ptr(),
+                  cl.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), keys[0].data_ptr(),
+                  ids[0].data_ptr(), keys[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(),
+                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), s)
+        ev1.record()
+        _timed(collector, "forward_render_time", ev0, ev1)
+        ids_sorted = ids[1].clone() if R > 0 else ids[1]  # let the 2R-entry scratch go back to the allocator
+        ctx.rs, ctx.R, ctx.P, ctx.collector = rs, R, P, collector
+        ctx.save_for_backward(rec, bg, cl, ranges, ids_sorted, final_T, n_contrib)
+        ctx.debug = dict(keys_sorted=keys[1], ids_sorted=ids_sorted, ranges=ranges, offsets=offsets, R=R) \
+            if os.environ.get("GS_B200_KEEP_BINNING") == "1" else None
+        n_render, n_consider, n_contrib_sum = stats[0], stats[1], stats[2]
+        ctx.mark_non_differentiable(n_render, n_consider, n_contrib_sum)
+        return image, n_render, n_consider, n_contrib_sum
+
+    @staticmethod
+    def backward(ctx, g_image, *_unused):
+        rec, bg, cl, ranges, ids_sorted, final_T, n_contrib = ctx.saved_tensors
+        rs, R, P = ctx.rs, ctx.R, ctx.P
+        H, W = int(rs.image_height), int(rs.image_width)
+        dev = rec.device
+        g_image = torch.zeros((3, H, W), dtype=torch.float32, device=dev) if g_image is None else _f32c(g_image, "grad")
+        d_means2D = torch.empty((P, 2), dtype=torch.float32, device=dev)
+        d_conic = torch.empty((P, 4), dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.call("gs_render_backward", P, R, H, W, rec.data_ptr(), bg.data_ptr(), cl.data_ptr(), ranges.data_ptr(),
+                  ids_sorted.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), g_image.data_ptr(),
+                  d_means2D.data_ptr(), d_conic.data_ptr(), d_rgb.data_ptr(), _stream())
+        ev1.record()
+        _timed(ctx.collector, "backward_render_time", ev0, ev1)
+        return d_means2D, d_conic, d_rgb, None, None, None, None, None
+
+
+def render_gaussians(means2D, conic_opacity, rgb, depths, radii, compute_locally, raster_settings, cuda_args=None,
+                     extended_compute_locally=None):
+    """-> (image (3,H,W) with non-local tiles exactly 0, n_render, n_consider, n_contrib)."""
+    collector = None
+    if isinstance(cuda_args, dict):
+        collector = cuda_args.setdefault("stats_collector", {})
+    return _RenderGaussians.apply(means2D, conic_opacity, rgb, depths, radii, compute_locally, raster_settings, collector)
+
+
+def get_local2j_ids_bool(image_height, image_width, rank, world_size, means2D, radii, dist_global_strategy,
+                         cuda_args=None):
+    """(P, world_size) bool: does splat i touch rank j's flattened tile range.  `rank` is unused (kept for
+    signature parity with workload_division.py:727-738)."""
+    means2D = _f32c(means2D.detach(), "means2D")
+    radii = radii.to(torch.int32).contiguous()
+    strat = dist_global_strategy.to(device=means2D.device, dtype=torch.int32).contiguous()
+    if strat.numel() != world_size + 1:
+        raise ValueError("dist_global_strategy must have world_size+1 entries")
+    P = means2D.shape[0]
+    out = torch.empty((P, world_size), dtype=torch.bool, device=means2D.device)
+    _lib.call("gs_get_local2j_ids_bool", P, int(image_height), int(image_width), int(world_size), means2D.data_ptr(),
+              radii.data_ptr(), strat.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def get_local2j_ids_bool_adjust_mode6(image_height, image_width, rank, world_size, means2D, radii, rectangles,
+                                      cuda_args=None):
+    """Legacy variant (workload_division.py:471-484): rank j owns tile rectangle (y_l, y_r, x_l, x_r)."""
+    means2D = _f32c(means2D.detach(), "means2D")
+    radii = radii.to(torch.int32).contiguous()
+    rects = rectangles.to(device=means2D.device, dtype=torch.int32).contiguous()
+    P = means2D.shape[0]
+    out = torch.empty((P, world_size), dtype=torch.bool, device=means2D.device)
+    _lib.call("gs_get_local2j_ids_bool_rects", P, int(image_height), int(image_width), int(world_size),
+              means2D.data_ptr(), radii.data_ptr(), rects.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def get_block_XY():
+    """(BLOCK_X, BLOCK_Y, ONE_DIM_BLOCK_SIZE) as compiled into the library (arguments/__init__.py:254-257)."""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _lib.call("gs_get_block_xy", C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+class _FusedL1SSIM(torch.autograd.Function):
+    """Per-strip (Ll1, ssim) of loss_distribution.py:2536-2585 in two kernels instead of ~20."""
+
+    @staticmethod
+    def forward(ctx, image, gt_u8, row0, row1):
+        image = _f32c(image, "image")
+        if gt_u8.dtype != torch.uint8 or not gt_u8.is_cuda:
+            raise TypeError("gt strip must be a CUDA uint8 tensor (3, rows, W)")
+        gt_u8 = gt_u8.contiguous()
+        _, H, W = image.shape
+        rows = row1 - row0
+        if tuple(gt_u8.shape) != (3, rows, W):
+            raise ValueError(f"gt strip must be (3,{rows},{W}), got {tuple(gt_u8.shape)}")
+        tb = _lib.query("gs_loss_temp_bytes", rows, W)
+        temp = torch.empty((tb,), dtype=torch.uint8, device=image.device)
+        out = torch.empty((2,), dtype=torch.float32, device=image.device)
+        _lib.call("gs_loss_forward", H, W, row0, row1, image.data_ptr(), gt_u8.data_ptr(), out.data_ptr(),
+                  temp.data_ptr(), tb, _stream())
+        ctx.rows = (row0, row1)
+        ctx.save_for_backward(image, gt_u8, temp)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_l1, g_ssim):
+        image, gt_u8, temp = ctx.saved_tensors
+        _, H, W = image.shape
+        row0, row1 = ctx.rows
+        dev = image.device
+        g_l1 = torch.zeros((), device=dev) if g_l1 is None else g_l1
+        g_ssim = torch.zeros((), device=dev) if g_ssim is None else g_ssim
+        g_l1, g_ssim = g_l1.to(torch.float32).contiguous(), g_ssim.to(torch.float32).contiguous()
+        d_image = torch.empty_like(image)
+        _lib.call("gs_loss_backward", H, W, row0, row1, image.data_ptr(), gt_u8.data_ptr(), temp.data_ptr(),
+                  g_l1.data_ptr(), g_ssim.data_ptr(), d_image.data_ptr(), _stream())
+        return d_image, None, None, None
+
+
+def fused_l1_ssim(image, gt_u8, row0, row1):
+    """-> (Ll1, ssim_loss) 0-dim tensors, both normalised by 3*H*W of the FULL image."""
+    return _FusedL1SSIM.apply(image, gt_u8, int(row0), int(row1))

@@ -1,0 +1,161 @@
+/*
+ * grendel_gs_b200.h -- C ABI of the B200-native (sm_100a) Gaussian rasterizer hot path.
+ *
+ * This is the drop-in boundary for the ONE path nyu-systems/Grendel-GS reaches through its
+ * `diff_gaussian_rasterization` extension.  Every entry point names the
+ * reference call site it replaces.  The reference binds these operators from Python, so the
+ * reference-side stub is a ctypes binding: INTEGRATION.md shows it, and
+ * grendel-gs_b200/diff_gaussian_rasterization/ is that binding, exporting the reference's own
+ * names (GaussianRasterizationSettings, GaussianRasterizer, _C.get_local2j_ids_bool, ...).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing is
+ *    synchronised unless stated;
+ *  - tensors are dense row-major fp32 / int32 / uint8 exactly as the reference passes them;
+ *  - return value 0 = success, otherwise a negative GS_E* code; gs_last_error() gives text;
+ *  - the library owns no persistent device memory: callers pass every workspace (sizes from the
+ *    gs_*_bytes queries), which keeps the operator re-entrant across the B rasterizer instances
+ *    that coexist in one training step (gaussian_renderer/__init__.py:919-963).
+ *  - gradient conventions (see oracle/gs_oracle.c:gso_preprocess_backward): dL_dmeans2D is per
+ *    NDC unit (pixel gradient * (W/2, H/2)), which is what densification.py:24 reads from
+ *    means2D.grad; dL_dconic_opacity holds true partials (dA, dB, dC, dOpacity).
+ */
+#ifndef GRENDEL_GS_B200_H
+#define GRENDEL_GS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_OK 0
+#define GS_EINVAL (-1)  /* bad argument */
+#define GS_ECUDA (-2)   /* CUDA runtime error; see gs_last_error() */
+#define GS_ENOMEM (-3)  /* workspace too small */
+
+#define GS_BLOCK_X 16
+#define GS_BLOCK_Y 16
+#define GS_ONE_DIM_BLOCK_SIZE 256
+#define GS_REC_FLOATS 12 /* packed per-splat record: 3 x float4 */
+
+#if defined(__GNUC__)
+#define GS_API __attribute__((visibility("default")))
+#else
+#define GS_API
+#endif
+
+/* Text of the last error raised on the calling thread. */
+GS_API const char *gs_last_error(void);
+
+/* Library / build identification, e.g. "grendel-gs_b200 sm_100a r1". */
+GS_API const char *gs_version(void);
+
+/* _C.get_block_XY()  -- /root/reference/arguments/__init__.py:254-257 */
+GS_API int gs_get_block_xy(int *block_x, int *block_y, int *one_dim_block_size);
+
+/* GaussianRasterizer.preprocess_gaussians forward (CUDA stage "10 preprocess")
+ * -- /root/reference/gaussian_renderer/__init__.py:949-956.
+ * means3D (P,3) scales (P,3, activated) rotations (P,4, normalised wxyz) opacities (P,1, activated)
+ * shs (P,16,3); viewmatrix/projmatrix (4,4) in the reference's transposed storage
+ * (scene/cameras.py:84-99); campos (3).
+ * out: means2D (P,2) pixels, depths (P), radii (P) int32 (0 = culled), conic_opacity (P,4),
+ * rgb (P,3), clamped (P) uint8 bit c = channel c clamped at 0.  All outputs are written for every
+ * splat (zeros when culled); no pre-initialisation needed. */
+GS_API int gs_preprocess_forward(int P, int sh_degree, const float *means3D, const float *scales, float scale_modifier,
+                          const float *rotations, const float *opacities, const float *shs, const float *viewmatrix,
+                          const float *projmatrix, const float *campos, int image_width, int image_height,
+                          float tanfovx, float tanfovy, float *means2D, float *depths, int32_t *radii,
+                          float *conic_opacity, float *rgb, uint8_t *clamped, void *stream);
+
+/* autograd backward of preprocess_gaussians (CUDA stage "b20 preprocess")
+ * -- /root/reference/train_internal.py:195 reaching gaussian_renderer/__init__.py:949-958.
+ * All five gradient outputs are written for every splat (zeros when culled). */
+GS_API int gs_preprocess_backward(int P, int sh_degree, const float *means3D, const float *scales, float scale_modifier,
+                           const float *rotations, const float *shs, const float *viewmatrix, const float *projmatrix,
+                           const float *campos, int image_width, int image_height, float tanfovx, float tanfovy,
+                           const int32_t *radii, const uint8_t *clamped, const float *dL_dmeans2D,
+                           const float *dL_dconic_opacity, const float *dL_drgb, float *dL_dmeans3D, float *dL_dscales,
+                           float *dL_drotations, float *dL_dopacities, float *dL_dshs, void *stream);
+
+/* _C.get_local2j_ids_bool -- /root/reference/gaussian_renderer/workload_division.py:721-744.
+ * strategy: (world_size+1) int32 ascending flattened tile ids; out: (P, world_size) uint8/bool. */
+GS_API int gs_get_local2j_ids_bool(int P, int image_height, int image_width, int world_size, const float *means2D,
+                            const int32_t *radii, const int32_t *strategy, uint8_t *out, void *stream);
+
+/* _C.get_local2j_ids_bool_adjust_mode6 -- workload_division.py:471-484 (legacy).
+ * rects: (world_size,4) int32 tile rectangles (y_l, y_r, x_l, x_r). */
+GS_API int gs_get_local2j_ids_bool_rects(int P, int image_height, int image_width, int world_size, const float *means2D,
+                                  const int32_t *radii, const int32_t *rects, uint8_t *out, void *stream);
+
+/* ---- GaussianRasterizer.render_gaussians -- gaussian_renderer/__init__.py:1271-1282 -------------
+ * Three calls because the number R of (splat, local tile) instances is data dependent:
+ *   gs_render_count   stages 21-24 + 30: per-splat LOCAL tile count, inclusive scan, packed records
+ *   gs_render_forward stages 40,50,60,70,81-83: duplicate-with-keys, radix sort, tile ranges, blend
+ *   gs_render_backward stage b10
+ */
+
+/* Bytes of scratch gs_render_count needs for P splats. */
+GS_API size_t gs_render_count_temp_bytes(int P);
+
+/* compute_locally: (TILE_Y*TILE_X) uint8/bool mask (workload_division.py:773-787).
+ * offsets: (P) uint32 inclusive prefix sum of local tiles touched.
+ * rec: (P, GS_REC_FLOATS) packed per-splat records consumed by the blend kernels.
+ * R_host: HOST pointer; receives the instance count.  This call synchronises `stream`. */
+GS_API int gs_render_count(int P, int image_height, int image_width, const float *means2D, const float *conic_opacity,
+                    const float *rgb, const int32_t *radii, const uint8_t *compute_locally, uint32_t *offsets,
+                    float *rec, void *temp, size_t temp_bytes, int64_t *R_host, void *stream);
+
+/* Bytes of radix-sort scratch for R instances. */
+GS_API size_t gs_render_sort_temp_bytes(int64_t R);
+
+/* keys_unsorted/keys_sorted: (R) uint64 = tile id << 32 | fp32 depth bits; ids_unsorted/ids_sorted: (R) uint32.
+ * ranges: (T,2) uint32 [start,end) per tile.  bg: (3).  image: (3,H,W) -- written in full: non-local
+ * tiles are exactly 0 (loss_distribution.py:1875).  final_T (H,W) f32 and n_contrib (H,W) uint32 are
+ * kept for the backward.  stats: optional (3) int64 sums of n_render / n_consider / n_contrib, or NULL. */
+GS_API int gs_render_forward(int P, int64_t R, int image_height, int image_width, const float *means2D, const float *depths,
+                      const int32_t *radii, const uint8_t *compute_locally, const uint32_t *offsets, const float *rec,
+                      const float *bg, uint64_t *keys_unsorted, uint32_t *ids_unsorted, uint64_t *keys_sorted,
+                      uint32_t *ids_sorted, void *sort_temp, size_t sort_temp_bytes, uint32_t *ranges, float *image,
+                      float *final_T, uint32_t *n_contrib, int64_t *stats, void *stream);
+
+/* dL_dimage: (3,H,W).  The three gradient outputs (P,2) (P,4) (P,3) are zero-filled and
+ * accumulated by this call. */
+GS_API int gs_render_backward(int P, int64_t R, int image_height, int image_width, const float *rec, const float *bg,
+                       const uint8_t *compute_locally, const uint32_t *ranges, const uint32_t *ids_sorted,
+                       const float *final_T, const uint32_t *n_contrib, const float *dL_dimage, float *dL_dmeans2D,
+                       float *dL_dconic_opacity, float *dL_drgb, void *stream);
+
+/* ---- per-strip loss -- gaussian_renderer/loss_distribution.py:2536-2585 + utils/loss_utils.py:88-132 ----
+ * image: (3,H,W) full-size render of which rows [row0,row1) are this rank's strip;
+ * gt_u8: (3,row1-row0,W) uint8 ground-truth strip (camera.original_image of loss_distribution.py:2561).
+ * out_l1_ssim: (2) float = { sum|x-y| , sum ssim_map } / (3*H*W)  -- the Ll1 and ssim_loss of :2571,2576.
+ * temp (gs_loss_temp_bytes) keeps three derivative maps for the backward.
+ * backward: dL_dimage (3,H,W) = grad_l1[0]*dLl1/dimage + grad_ssim[0]*dssim/dimage, with grad_* DEVICE
+ * scalars (the autograd upstream gradients; no host sync); rows outside the strip are written 0. */
+GS_API size_t gs_loss_temp_bytes(int rows, int image_width);
+GS_API int gs_loss_forward(int image_height, int image_width, int row0, int row1, const float *image, const uint8_t *gt_u8,
+                    float *out_l1_ssim, void *temp, size_t temp_bytes, void *stream);
+GS_API int gs_loss_backward(int image_height, int image_width, int row0, int row1, const float *image, const uint8_t *gt_u8,
+                     const void *temp, const float *grad_l1, const float *grad_ssim, float *dL_dimage, void *stream);
+
+/* ---- all-to-all staging -- gaussian_renderer/__init__.py:590-607,651-658 --------------------------
+ * Pack the splats flagged for destination j (mask column j of gs_get_local2j_ids_bool, row stride
+ * world_size) into a dense send buffer of 11-float rows (means2D 2, rgb 3, conic_opacity 4, radius
+ * as float, depth), keeping splat order.  pos: (P) int32 exclusive rank of each flagged splat
+ * (from gs_mask_scan).  The backward scatters 9-float gradient rows back. */
+GS_API size_t gs_mask_scan_temp_bytes(int P);
+GS_API int gs_mask_scan(int P, int world_size, int column, const uint8_t *mask, int32_t *pos, int32_t *count, void *temp,
+                 size_t temp_bytes, void *stream);
+GS_API int gs_pack_rows(int P, int world_size, int column, const uint8_t *mask, const int32_t *pos, const float *means2D,
+                 const float *rgb, const float *conic_opacity, const int32_t *radii, const float *depths, float *out,
+                 void *stream);
+GS_API int gs_unpack_rows(int n, const float *rows, float *means2D, float *rgb, float *conic_opacity, int32_t *radii,
+                   float *depths, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRENDEL_GS_B200_H */
