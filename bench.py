@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- training-step throughput of the rasterizer hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A "step" is one pass of the hot path over one batch of synthetic input: activations -> preprocess ->
+(all-to-all) -> tile binning + sort -> alpha blend -> fused L1+SSIM -> backward of all of it
+(/root/reference/train_internal.py:139-196 minus optimizer / densification).
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition of every key.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "grendel-gs_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "train-step Gaussians/s (preprocess+forward+loss+backward)"
+UNIT = "Gaussians/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", help="c2 = 2M Gaussians @1920x1080 (BASELINE.json configs[1])")
+    ap.add_argument("--n", type=int, default=0, help="override Gaussian count")
+    ap.add_argument("--cpu-sample", type=int, default=250_000, help="Gaussians in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from gs_b200 import synthetic as syn
+    cfg = dict(syn.CONFIGS[args.workload])
+    if args.n:
+        cfg["n"] = args.n
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); smax.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        med = float(np.median(sm)) if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (kind "port": the reference has no CPU path and its CUDA source is absent)
+# ---------------------------------------------------------------------------------------------------
+def cpu_arm(cfg, sample_n, steps, warmup):
+    from gs_b200 import synthetic as syn
+    from oracle.oracle import Oracle
+    cores = os.cpu_count() or 1
+    o = Oracle(np.float32, threads=cores)
+    W, H = cfg["width"], cfg["height"]
+    n = min(sample_n, cfg["n"])
+    cam = syn.make_camera(W, H)
+    sc = syn.make_scene(n, W, H, seed=0)
+    gt = syn.make_gt_image(W, H)
+    for _ in range(warmup):
+        o.train_step(sc, cam, gt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.train_step(sc, cam, gt)
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=n / dt, unit=UNIT, cores=cores, kind="port", ms_per_step=dt * 1e3,
+                sample=f"{n} of {cfg['n']} Gaussians (seed 0, same distribution) on the full {W}x{H} view, "
+                       f"forward+loss+backward, oracle/gs_oracle.c with OpenMP on {cores} threads")
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path timed on the host cores.  The reference ships no
+    CPU path and its CUDA rasterizer source is an absent submodule, so this arm is the
+    oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload(args)
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    r = cpu_arm(cfg, args.cpu_sample, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfg['n']} Gaussians @ {cfg['width']}x{cfg['height']}, bounded CPU sample"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def alg_bytes(N, V, Vp, R, P, T):
+    """Algorithmic (compulsory) bytes per stage, SURVEY.md section 8(d)."""
+    return {"10 preprocess": 16 * N + 292 * V, "binning": 44 * Vp + 44 * R + 8 * T, "70 render": 40 * R + 20 * P,
+            "loss": 27 * P, "b10 render": 76 * R + 20 * P, "b20 preprocess": 304 * V + 236 * N}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gs_b200 import _lib, pipeline, synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    cfg = workload(args)
+    W, H, N = cfg["width"], cfg["height"], cfg["n"]
+    B = world  # one view per GPU per step: weak scaling in views, Gaussians sharded (README.md:344 "4 GPU bsz 4")
+    P_pix, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    scene = syn.make_scene(N, W, H, seed=0)
+    cams = syn.make_batch_cameras(W, H, B)
+    gts = [torch.from_numpy(syn.make_gt_image(W, H, seed=1 + k)).pin_memory() for k in range(B)]
+    trainer = pipeline.Trainer(scene, cams, gts, dev, rank, world)
+    del scene
+
+    def barrier_sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: inputs resident in HBM --------------------------------------------------------
+    for _ in range(warmup):
+        trainer.step(resident=True)
+    barrier_sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync()
+    e0.record()
+    for _ in range(steps):
+        trainer.step(resident=True)
+    e1.record()
+    barrier_sync()
+    ms = e0.elapsed_time(e1)
+    stages = _lib.profile_read()
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / steps
+    info = trainer.last_info()  # realised V, V', R on this rank
+
+    # ---- leg 2: end to end through the public operator with HOST buffers ------------------------
+    for _ in range(2):
+        trainer.step(resident=False)
+    barrier_sync()
+    e0.record()
+    for _ in range(steps):
+        loss_host = trainer.step(resident=False)
+    e1.record()
+    barrier_sync()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item()) / steps
+    h2d, d2h = trainer.io_bytes_per_step()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    ab = alg_bytes(N // world * B, info["V"], info["Vp"], info["R"], info["P_local"], T * B)
+    per_stage = {k: v[0] / v[1] for k, v in stages.items()}
+    launches = {k: v[1] for k, v in stages.items()}
+    key_of = {"10 preprocess": "10 preprocess", "70 render": "70 render", "b10 render": "b10 render",
+              "b20 preprocess": "b20 preprocess"}
+    dom = max(per_stage, key=per_stage.get)
+    units = max(1, launches[dom] // steps)  # launches of that stage per step (one per camera)
+    if dom in key_of:
+        dom_bytes = ab[key_of[dom]] / units
+    elif dom.startswith("loss"):
+        dom_bytes = ab["loss"] / units / 2
+    else:
+        dom_bytes = ab["binning"] / units
+    achieved = dom_bytes / (per_stage[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": per_stage[dom],
+                "stage_ms_per_launch": {k: round(v, 4) for k, v in per_stage.items()},
+                "step_alg_bytes": float(sum(ab.values())),
+                "step_frac_of_hbm_roofline": float(sum(ab.values())) / (ms_step * 1e-3) / 1e9 / peak}
+
+    value = N * B / (ms_step * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {N} Gaussians (sh_degree 3) @ {W}x{H}, {B} view(s)/step, "
+                                   f"Gaussians sharded {world} way(s), pixels sharded by tile rows",
+                       "views_per_step": B, "views_per_s": B / (ms_step * 1e-3), "visible": info["V"],
+                       "instances_R": info["R"], "l2_policy": "inputs (472 MB parameters + 0.4 GB binning state) exceed the 126 MB L2",
+                       "loss_check": loss_host},
+            "e2e": {"value": N * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(sum(launches.values())), "roofline": roofline, "clocks": clocks}
+    if not args.no_cpu_baseline:
+        r = cpu_arm(cfg, args.cpu_sample, 1, 1)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

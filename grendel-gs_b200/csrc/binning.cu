@@ -108,10 +108,16 @@ extern "C" int gs_render_count(int P, int image_height, int image_width, const f
     char *scan_temp = (char *)temp + align_up((size_t)P * sizeof(uint32_t), 256);
     size_t scan_bytes = temp_bytes - align_up((size_t)P * sizeof(uint32_t), 256);
     const int grid = (P + BIN_THREADS - 1) / BIN_THREADS;
-    k_count_tiles<<<grid, BIN_THREADS, 0, stream>>>(P, image_width, image_height, means2D, conic_opacity, rgb, radii,
-                                                    compute_locally, touched, rec);
-    GS_LAUNCH_CHECK();
-    GS_CUDA_TRY(cub::DeviceScan::InclusiveSum(scan_temp, scan_bytes, touched, offsets, P, stream));
+    {
+        GsStageTimer timer(GS_STAGE_COUNT_TILES, stream);
+        k_count_tiles<<<grid, BIN_THREADS, 0, stream>>>(P, image_width, image_height, means2D, conic_opacity, rgb, radii,
+                                                        compute_locally, touched, rec);
+        GS_LAUNCH_CHECK();
+    }
+    {
+        GsStageTimer timer(GS_STAGE_SCAN, stream);
+        GS_CUDA_TRY(cub::DeviceScan::InclusiveSum(scan_temp, scan_bytes, touched, offsets, P, stream));
+    }
     uint32_t last = 0;
     GS_CUDA_TRY(cudaMemcpyAsync(&last, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     GS_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -158,13 +164,22 @@ extern "C" int gs_render_forward(int P, int64_t R, int image_height, int image_w
             gs_set_error("gs_render_forward: sort temp too small");
             return GS_ENOMEM;
         }
-        k_duplicate<<<(P + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, stream>>>(
-            P, image_width, image_height, means2D, depths, radii, compute_locally, offsets, keys_unsorted, ids_unsorted);
-        GS_LAUNCH_CHECK();
-        GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_unsorted, keys_sorted,
-                                                    ids_unsorted, ids_sorted, R, 0, key_bits(T), stream));
-        k_tile_ranges<<<(unsigned)((R + BIN_THREADS - 1) / BIN_THREADS), BIN_THREADS, 0, stream>>>(R, keys_sorted, ranges);
-        GS_LAUNCH_CHECK();
+        {
+            GsStageTimer timer(GS_STAGE_DUPLICATE, stream);
+            k_duplicate<<<(P + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, stream>>>(
+                P, image_width, image_height, means2D, depths, radii, compute_locally, offsets, keys_unsorted, ids_unsorted);
+            GS_LAUNCH_CHECK();
+        }
+        {
+            GsStageTimer timer(GS_STAGE_SORT, stream);
+            GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_unsorted, keys_sorted,
+                                                        ids_unsorted, ids_sorted, R, 0, key_bits(T), stream));
+        }
+        {
+            GsStageTimer timer(GS_STAGE_RANGES, stream);
+            k_tile_ranges<<<(unsigned)((R + BIN_THREADS - 1) / BIN_THREADS), BIN_THREADS, 0, stream>>>(R, keys_sorted, ranges);
+            GS_LAUNCH_CHECK();
+        }
     }
     return gs_launch_blend_forward(R, image_height, image_width, rec, bg, compute_locally, ranges, ids_sorted, image,
                                    final_T, n_contrib, stats, stream);

@@ -293,6 +293,7 @@ int gs_launch_blend_forward(int64_t R, int H, int W, const float *rec, const flo
     (void)R;
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     if (stats) GS_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t), stream));
+    GsStageTimer timer(GS_STAGE_BLEND_FWD, stream);
     k_blend_fwd<<<gx * gy, BL_THREADS, 0, stream>>>(W, H, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
                                                     reinterpret_cast<const uint2 *>(ranges), ids_sorted, image, final_T,
                                                     n_contrib, reinterpret_cast<unsigned long long *>(stats));
@@ -315,6 +316,7 @@ extern "C" int gs_render_backward(int P, int64_t R, int image_height, int image_
     if (R == 0) return GS_OK;
     GS_REQUIRE(rec && bg && compute_locally && ranges && ids_sorted && final_T && n_contrib && dL_dimage, "null input");
     const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
+    GsStageTimer timer(GS_STAGE_BLEND_BWD, stream);
     k_blend_bwd<<<gx * gy, BL_THREADS, 0, stream>>>(image_width, image_height, reinterpret_cast<const float4 *>(rec), bg,
                                                     compute_locally, reinterpret_cast<const uint2 *>(ranges), ids_sorted,
                                                     final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity,

@@ -25,3 +25,60 @@ extern "C" int gs_get_block_xy(int *block_x, int *block_y, int *one_dim_block_si
     *one_dim_block_size = GS_ONE_DIM_BLOCK_SIZE;
     return GS_OK;
 }
+
+// ---- per-stage device timing -------------------------------------------------------------------
+#include <vector>
+bool g_gs_profile_on = false;
+namespace {
+struct StageRec {
+    std::vector<cudaEvent_t> begin, end;  // event pool, reused across reads
+    size_t used = 0;
+};
+StageRec g_stage[GS_STAGE_NUM];
+const char *kStageNames[GS_STAGE_NUM] = {
+    "10 preprocess", "21-24 count local tiles", "30 InclusiveSum", "40 duplicateWithKeys", "50 SortPairs",
+    "60 identifyTileRanges", "70 render", "b10 render", "b20 preprocess", "loss forward", "loss backward",
+    "get_local2j_ids_bool", "all2all pack", "all2all unpack"};
+}  // namespace
+
+void gs_prof_mark(int stage, bool begin, cudaStream_t stream) {
+    StageRec &r = g_stage[stage];
+    if (begin) {
+        if (r.used == r.begin.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            r.begin.push_back(a);
+            r.end.push_back(b);
+        }
+        cudaEventRecord(r.begin[r.used], stream);
+    } else {
+        if (r.used < r.end.size()) cudaEventRecord(r.end[r.used++], stream);
+    }
+}
+
+extern "C" int gs_profile_enable(int on) {
+    g_gs_profile_on = on != 0;
+    if (on)
+        for (int s = 0; s < GS_STAGE_NUM; s++) g_stage[s].used = 0;
+    return GS_OK;
+}
+
+extern "C" int gs_profile_read(int stage, double *total_ms, int64_t *launches) {
+    GS_REQUIRE(stage >= 0 && stage < GS_STAGE_NUM && total_ms && launches, "stage");
+    StageRec &r = g_stage[stage];
+    double tot = 0.0;
+    for (size_t k = 0; k < r.used; k++) {
+        GS_CUDA_TRY(cudaEventSynchronize(r.end[k]));
+        float ms = 0.f;
+        GS_CUDA_TRY(cudaEventElapsedTime(&ms, r.begin[k], r.end[k]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)r.used;
+    r.used = 0;
+    return GS_OK;
+}
+
+extern "C" const char *gs_profile_stage_name(int stage) {
+    return (stage >= 0 && stage < GS_STAGE_NUM) ? kStageNames[stage] : "?";
+}

@@ -28,6 +28,15 @@ void gs_set_error(const char *fmt, ...);
         }                                                               \
     } while (0)
 
+// ---- per-stage device timing (capi.cu) -------------------------------------------------------------
+extern bool g_gs_profile_on;
+void gs_prof_mark(int stage, bool begin, cudaStream_t stream);
+struct GsStageTimer {  // RAII: events around the launches of one stage when profiling is enabled
+    int stage; cudaStream_t stream;
+    GsStageTimer(int st, cudaStream_t s) : stage(st), stream(s) { if (g_gs_profile_on) gs_prof_mark(stage, true, stream); }
+    ~GsStageTimer() { if (g_gs_profile_on) gs_prof_mark(stage, false, stream); }
+};
+
 // ---- tile rectangle of a splat ----------------------------------------------------------------
 // Same IEEE fp32 operation sequence as oracle/gs_oracle.c:get_rect -> tile indices are bit-exact.
 GS_D void gs_get_rect(float px, float py, int r, int gx, int gy, int &x0, int &y0, int &x1, int &y1) {

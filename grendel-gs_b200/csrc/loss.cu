@@ -181,6 +181,7 @@ extern "C" int gs_loss_forward(int image_height, int image_width, int row0, int 
     float *maps = (float *)((char *)temp + 256);
     GS_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), stream));
     dim3 grid((image_width + LS_TILE - 1) / LS_TILE, (rows + LS_TILE - 1) / LS_TILE);
+    GsStageTimer timer(GS_STAGE_LOSS_FWD, stream);
     k_loss_fwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, image, gt_u8, maps, sums);
     GS_LAUNCH_CHECK();
     k_loss_finalize<<<1, 1, 0, stream>>>(sums, 1.0 / (3.0 * (double)image_height * (double)image_width), out_l1_ssim);
@@ -207,6 +208,7 @@ extern "C" int gs_loss_backward(int image_height, int image_width, int row0, int
                                         sizeof(float) * (size_t)(image_height - row1) * image_width, stream));
     }
     dim3 grid((image_width + LS_TILE - 1) / LS_TILE, (rows + LS_TILE - 1) / LS_TILE);
+    GsStageTimer timer(GS_STAGE_LOSS_BWD, stream);
     k_loss_bwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, image, gt_u8, maps, grad_l1,
                                                 grad_ssim, (float)(1.0 / (3.0 * (double)image_height * (double)image_width)),
                                                 dL_dimage);

@@ -437,6 +437,7 @@ extern "C" int gs_preprocess_forward(int P, int sh_degree, const float *means3D,
                    ((uintptr_t)means2D & 7) == 0,
                "shs/rotations/conic_opacity must be 16-byte aligned");
     const int grid = (P + PP_THREADS - 1) / PP_THREADS;
+    GsStageTimer timer(GS_STAGE_PREPROCESS_FWD, (cudaStream_t)stream);
     k_preprocess_fwd<<<grid, PP_THREADS, 0, (cudaStream_t)stream>>>(
         P, sh_degree, means3D, scales, scale_modifier, rotations, opacities, shs, viewmatrix, projmatrix, campos,
         image_width, image_height, tanfovx, tanfovy, means2D, depths, radii, conic_opacity, rgb, clamped);
@@ -463,6 +464,7 @@ extern "C" int gs_preprocess_backward(int P, int sh_degree, const float *means3D
                    ((uintptr_t)dL_dmeans2D & 7) == 0,
                "16-byte alignment");
     const int grid = (P + PP_THREADS - 1) / PP_THREADS;
+    GsStageTimer timer(GS_STAGE_PREPROCESS_BWD, (cudaStream_t)stream);
     k_preprocess_bwd<<<grid, PP_THREADS, 0, (cudaStream_t)stream>>>(
         P, sh_degree, means3D, scales, scale_modifier, rotations, shs, viewmatrix, projmatrix, campos, image_width,
         image_height, tanfovx, tanfovy, radii, clamped, dL_dmeans2D, dL_dconic_opacity, dL_drgb, dL_dmeans3D,

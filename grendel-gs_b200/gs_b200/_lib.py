@@ -30,13 +30,18 @@ SIGNATURES = {
     "gs_render_forward": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_render_backward": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_profile_enable": (_i, [_i]),
+    "gs_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "gs_profile_stage_name": (C.c_char_p, [_i]),
     "gs_loss_temp_bytes": (_sz, [_i, _i]),
     "gs_loss_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gs_loss_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gs_mask_scan_temp_bytes": (_sz, [_i]),
-    "gs_mask_scan": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "gs_pack_rows": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gs_unpack_rows": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_route_scan_temp_bytes": (_sz, [_i, _i]),
+    "gs_route_scan": (_i, [_i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gs_pack_rows": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_unpack_rows": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_pack_grad_rows": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_scatter_grad_rows": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -80,3 +85,21 @@ def query(name, *args):
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+STAGE_NUM = 14
+
+
+def profile_enable(on=True):
+    call("gs_profile_enable", 1 if on else 0)
+
+
+def profile_read():
+    """-> {stage name: (total ms, launches)} for every stage that recorded launches; resets the counters."""
+    out = {}
+    for st in range(STAGE_NUM):
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        call("gs_profile_read", st, C.byref(ms), C.byref(n))
+        if n.value:
+            out[load().gs_profile_stage_name(st).decode()] = (ms.value, n.value)
+    return out

@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 BLOCK_X, BLOCK_Y, ONE_DIM_BLOCK_SIZE = 16, 16, 256
+LAST_R_TOTAL = 0  # instances binned by the most recent render_gaussians calls (reset by the caller)
 
 
 def _stream():
@@ -190,6 +191,8 @@ class _RenderGaussians(torch.autograd.Function):
                   radii.data_ptr(), cl.data_ptr(), offsets.data_ptr(), rec.data_ptr(), temp.data_ptr(), tb,
                   C.byref(R), s)
         R = int(R.value)
+        global LAST_R_TOTAL
+        LAST_R_TOTAL += R
         Ra = max(R, 1)
         keys = torch.empty((2, Ra), dtype=torch.int64, device=dev)
         ids = torch.empty((2, Ra), dtype=torch.int32, device=dev)

@@ -10,13 +10,12 @@ The reference's own Python (gaussian_renderer/*.py) runs unchanged on top of the
   * one sparse all-to-all of projected splats per step and its mirror in backward
     (gaussian_renderer/__init__.py:542-698).
 """
-import math
 
 import torch
 import torch.nn as nn
 
 from . import ops
-from .division import DivisionStrategy, start_strategy  # noqa: F401
+from .division import DivisionStrategy, StrategyHistory, start_strategy  # noqa: F401
 
 
 class RasterSettings:
@@ -103,3 +102,107 @@ def train_step_single(params, dcam, gt_u8_dev, lambda_dssim=0.2, collector=None,
     loss = (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - ss)
     loss.backward()
     return loss, means2D, radii
+
+
+class Trainer:
+    """Distributed training-step harness (one process per GPU).
+
+    Gaussians are sharded evenly by contiguous chunks (scene/gaussian_model.py:181-194); the B cameras of a
+    step are divided into tile-row strips over the W ranks (division.start_strategy); projected splats reach
+    their strip owners through exchange.exchange (skipped when W == 1, like gaussian_renderer/__init__.py:968).
+    """
+
+    def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None):
+        from . import exchange as _ex
+        self._ex = _ex
+        self.device, self.rank, self.world, self.group = device, rank, world, group
+        self.lambda_dssim = lambda_dssim
+        n = scene["means3D"].shape[0]
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        self.params = GaussianParams({k: v[lo:hi] for k, v in scene.items()}, device)
+        self.n_local, self.n_total = hi - lo, n
+        self.dcams = [DeviceCamera(c, device) for c in cams]
+        self.H, self.W = self.dcams[0].image_height, self.dcams[0].image_width
+        self.tile_y, self.tile_x = (self.H + 15) // 16, (self.W + 15) // 16
+        self.gts_host = gts_pinned                      # uint8 (3,H,W) pinned host tensors
+        self.gts_dev = [g.to(device) for g in gts_pinned]   # copies for the "inputs resident" leg
+        self.history = StrategyHistory([c.uid for c in self.dcams], self.tile_y, world)
+        self._strip_cache = {}
+        self._loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
+        self._info = {}
+        self._h2d = 0
+
+    # -- ground truth strips (load_camera_from_cpu_to_all_gpu, loss_distribution.py:2395-2533) ------------
+    def _gt_strip(self, k, y0, y1, resident):
+        key = (k, y0, y1, resident)
+        if resident:
+            if key not in self._strip_cache:
+                self._strip_cache[key] = self.gts_dev[k][:, y0:y1, :].contiguous()
+            return self._strip_cache[key]
+        if key not in self._strip_cache:  # pinned, contiguous staging copy of the strip rows
+            self._strip_cache[key] = self.gts_host[k][:, y0:y1, :].contiguous().pin_memory()
+        h = self._strip_cache[key]
+        self._h2d += h.numel()
+        return h.to(self.device, non_blocking=True)
+
+    def step(self, resident=True):
+        """One forward + loss + backward over the batch.  resident=False copies the GT strips from pinned host
+        memory inside the step and reads the loss back (the end-to-end leg); returns the loss as a float then."""
+        ops_ = ops
+        p = self.params
+        for t in p.raw_parameters():
+            t.grad = None
+        self._h2d = 0
+        ops.LAST_R_TOTAL = 0
+        uids = [c.uid for c in self.dcams]
+        strategies, _tasks = start_strategy(uids, self.history, self.world, self.rank)
+        settings = [c.settings(p.active_sh_degree) for c in self.dcams]
+        xyz, scaling, rotation, feats, opacity = p.get_xyz, p.get_scaling, p.get_rotation, p.get_features, p.get_opacity
+        collectors = [{} for _ in self.dcams]
+        screen = []
+        V = 0
+        for k, rs in enumerate(settings):
+            out = ops_.preprocess_gaussians(xyz, scaling, rotation, feats, opacity, rs, {"stats_collector": collectors[k]})
+            out[0].retain_grad()
+            screen.append(out)
+        self.means2D = [s[0] for s in screen]
+        if self.world > 1:
+            redistributed, cnt = self._ex.exchange(screen, strategies, settings, self.world, self.rank, self.group)
+        else:
+            redistributed = screen
+        loss_sum = None
+        Vp = Pl = 0
+        for k, st in enumerate(strategies):
+            rows = st.local_rows()
+            if rows is None:
+                continue
+            m2, rgb, co, radii, depths = redistributed[k]
+            cl = st.get_compute_locally(self.tile_x, self.device)
+            image, *_ = ops_.render_gaussians(m2, co, rgb, depths, radii, cl, settings[k],
+                                              {"stats_collector": collectors[k]})
+            y0, y1 = st.local_pixel_rows(self.H)
+            l1, ss = ops_.fused_l1_ssim(image, self._gt_strip(k, y0, y1, resident), y0, y1)
+            loss = (1.0 - self.lambda_dssim) * l1 + self.lambda_dssim * (1.0 - ss)
+            loss_sum = loss if loss_sum is None else loss_sum + loss
+            Vp += m2.shape[0]
+            Pl += (y1 - y0) * self.W
+        loss_sum.backward()
+        self._collectors, self._strategies = collectors, strategies
+        self._counts = dict(Vp=Vp, P_local=Pl, screen=screen)
+        if resident:
+            return None
+        self._loss_host.copy_(loss_sum.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_host[0])
+
+    def last_info(self):
+        """Realised sizes of the last step on this rank: V visible, V' splats rendered, R instances."""
+        V = sum(int((s[3] > 0).sum()) for s in self._counts["screen"])
+        R = ops.LAST_R_TOTAL
+        return dict(V=V, Vp=self._counts["Vp"], P_local=self._counts["P_local"], R=R)
+
+    def io_bytes_per_step(self):
+        """(host->device, device->host) bytes of the last resident=False step: GT strips in, loss out
+        (+ the 8-byte instance count each render reads back)."""
+        renders = sum(1 for st in self._strategies if st.local_rows() is not None)
+        return int(self._h2d), 4 + 8 * renders

@@ -128,6 +128,32 @@ GS_API int gs_render_backward(int P, int64_t R, int image_height, int image_widt
                        const float *final_T, const uint32_t *n_contrib, const float *dL_dimage, float *dL_dmeans2D,
                        float *dL_dconic_opacity, float *dL_drgb, void *stream);
 
+/* ---- per-kernel device timing ------------------------------------------------------------------
+ * The reference's fork logs per-stage GPU times under --zhx_time ("10 preprocess time: 0.29 ms", ...;
+ * /root/reference/analyze_statistic.py:1972-1991).  When enabled, every launch site brackets its
+ * kernel(s) with CUDA events on the launching stream; gs_profile_read synchronises those events and
+ * returns the accumulated milliseconds and launch count of one stage, then resets it. */
+enum {
+    GS_STAGE_PREPROCESS_FWD = 0, /* "10 preprocess" */
+    GS_STAGE_COUNT_TILES,        /* "21-24 updateDistributedStatLocally" */
+    GS_STAGE_SCAN,               /* "30 InclusiveSum" */
+    GS_STAGE_DUPLICATE,          /* "40 duplicateWithKeys" */
+    GS_STAGE_SORT,               /* "50 SortPairs" */
+    GS_STAGE_RANGES,             /* "60 identifyTileRanges" */
+    GS_STAGE_BLEND_FWD,          /* "70 render" */
+    GS_STAGE_BLEND_BWD,          /* "b10 render" */
+    GS_STAGE_PREPROCESS_BWD,     /* "b20 preprocess" */
+    GS_STAGE_LOSS_FWD,
+    GS_STAGE_LOSS_BWD,
+    GS_STAGE_LOCAL2J,
+    GS_STAGE_PACK,
+    GS_STAGE_UNPACK,
+    GS_STAGE_NUM
+};
+GS_API int gs_profile_enable(int on);
+GS_API int gs_profile_read(int stage, double *total_ms, int64_t *launches);
+GS_API const char *gs_profile_stage_name(int stage);
+
 /* ---- per-strip loss -- gaussian_renderer/loss_distribution.py:2536-2585 + utils/loss_utils.py:88-132 ----
  * image: (3,H,W) full-size render of which rows [row0,row1) are this rank's strip;
  * gt_u8: (3,row1-row0,W) uint8 ground-truth strip (camera.original_image of loss_distribution.py:2561).
@@ -142,18 +168,28 @@ GS_API int gs_loss_backward(int image_height, int image_width, int row0, int row
                      const void *temp, const float *grad_l1, const float *grad_ssim, float *dL_dimage, void *stream);
 
 /* ---- all-to-all staging -- gaussian_renderer/__init__.py:590-607,651-658 --------------------------
- * Pack the splats flagged for destination j (mask column j of gs_get_local2j_ids_bool, row stride
- * world_size) into a dense send buffer of 11-float rows (means2D 2, rgb 3, conic_opacity 4, radius
- * as float, depth), keeping splat order.  pos: (P) int32 exclusive rank of each flagged splat
- * (from gs_mask_scan).  The backward scatters 9-float gradient rows back. */
-GS_API size_t gs_mask_scan_temp_bytes(int P);
-GS_API int gs_mask_scan(int P, int world_size, int column, const uint8_t *mask, int32_t *pos, int32_t *count, void *temp,
-                 size_t temp_bytes, void *stream);
-GS_API int gs_pack_rows(int P, int world_size, int column, const uint8_t *mask, const int32_t *pos, const float *means2D,
-                 const float *rgb, const float *conic_opacity, const int32_t *radii, const float *depths, float *out,
-                 void *stream);
-GS_API int gs_unpack_rows(int n, const float *rows, float *means2D, float *rgb, float *conic_opacity, int32_t *radii,
-                   float *depths, void *stream);
+ * Replaces the per-(destination, camera) nonzero() + index_select + torch.cat glue around the sparse
+ * all-to-all.  For ONE camera with routing mask (P, ncols) from gs_get_local2j_ids_bool:
+ *   gs_route_scan        exclusive ranks of every flagged (column, splat) + per-column starts
+ *   gs_pack_rows         dense 11-float rows (means2D 2, rgb 3, conic_opacity 4, radius as float, depth)
+ *                        per destination column, splat order kept, written at HOST-given row offsets
+ *   gs_unpack_rows       received segments (one per source rank) -> the camera's operator inputs
+ *   gs_pack_grad_rows    backward of unpack: (n,2)(n,3)(n,4) gradients -> 9-float rows
+ *   gs_scatter_grad_rows backward of pack: each local splat sums the rows of the columns it went to
+ * ncols <= 16.  *_host arguments are HOST int32 arrays (passed to the kernels by value). */
+GS_API size_t gs_route_scan_temp_bytes(int P, int ncols);
+GS_API int gs_route_scan(int P, int ncols, const uint8_t *mask, int32_t *gpos, int32_t *colstart, void *temp,
+                         size_t temp_bytes, void *stream);
+GS_API int gs_pack_rows(int P, int ncols, const uint8_t *mask, const int32_t *gpos, const int32_t *colstart,
+                        const int32_t *dst_off_host, const float *means2D, const float *rgb, const float *conic_opacity,
+                        const int32_t *radii, const float *depths, float *out, void *stream);
+GS_API int gs_unpack_rows(int nseg, const int32_t *seg_off_host, const int32_t *seg_len_host, const float *rows,
+                          float *means2D, float *rgb, float *conic_opacity, int32_t *radii, float *depths, void *stream);
+GS_API int gs_pack_grad_rows(int nseg, const int32_t *seg_off_host, const int32_t *seg_len_host, const float *d_means2D,
+                             const float *d_rgb, const float *d_conic_opacity, float *rows, void *stream);
+GS_API int gs_scatter_grad_rows(int P, int ncols, const uint8_t *mask, const int32_t *gpos, const int32_t *colstart,
+                                const int32_t *src_off_host, const float *rows, float *d_means2D, float *d_rgb,
+                                float *d_conic_opacity, void *stream);
 
 #ifdef __cplusplus
 }
