@@ -11,8 +11,13 @@
 
 #define BIN_THREADS 256
 
-// Stages 21-24: per-splat number of LOCAL tiles its rectangle touches + the packed 48-byte record
-// the blend kernels gather (r0 = mx,my,A,B  r1 = C,opacity,ln(1/(255*opacity)),r  r2 = g,b,0,0).
+// Stages 21-24: per-splat number of LOCAL tiles its rectangle touches + the packed 48-byte record the
+// blend kernels gather:
+//   r0 = (mx, my, a', b')      a' = -A/2, b' = -B, c' = -C/2  so that  power = a'dx^2 + b'dx dy + c'dy^2
+//   r1 = (c', opacity, thr, red)     thr = ln(1/(255*opacity)) - margin: power < thr  =>  alpha < 1/255
+//   r2 = (green, blue, ex, ey)       half extents of the bounding box of {power >= thr} (+0.5 px slack),
+//                                    used by the blend kernels to cull splats per 8x4 pixel block
+#define GS_THR_MARGIN 0.02f
 __global__ void __launch_bounds__(BIN_THREADS)
 k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const float *__restrict__ conic_opacity,
               const float *__restrict__ rgb, const int32_t *__restrict__ radii,
@@ -35,10 +40,21 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     if (n > 0) {
         const float4 co = *reinterpret_cast<const float4 *>(conic_opacity + 4 * i);
-        r0 = make_float4(m.x, m.y, co.x, co.y);
-        // alpha < 1/255  <=>  power < ln(1/(255*opacity)); used (with a safety margin) to skip exp()
-        r1 = make_float4(co.z, co.w, -logf(255.0f * fmaxf(co.w, 1e-30f)), rgb[3 * i]);
-        r2 = make_float4(rgb[3 * i + 1], rgb[3 * i + 2], 0.f, 0.f);
+        const float thr = -logf(255.0f * fmaxf(co.w, 1e-30f)) - GS_THR_MARGIN;
+        // {d : A dx^2 + 2B dx dy + C dy^2 <= -2 thr} has half extents sqrt(t C/det), sqrt(t A/det)
+        const float t = -2.f * thr, det = co.x * co.z - co.y * co.y;
+        float ex = -1.f, ey = -1.f;  // never contributes
+        if (t > 0.f) {
+            if (det > 0.f && co.x > 0.f && co.z > 0.f) {
+                ex = sqrtf(t * co.z / det) * 1.001f + 0.5f;
+                ey = sqrtf(t * co.x / det) * 1.001f + 0.5f;
+            } else {
+                ex = ey = 3.0e38f;  // degenerate conic: never cull
+            }
+        }
+        r0 = make_float4(m.x, m.y, -0.5f * co.x, -co.y);
+        r1 = make_float4(-0.5f * co.z, co.w, thr, rgb[3 * i]);
+        r2 = make_float4(rgb[3 * i + 1], rgb[3 * i + 2], ex, ey);
     }
     float4 *o = reinterpret_cast<float4 *>(rec + (size_t)GS_REC_FLOATS * i);
     o[0] = r0; o[1] = r1; o[2] = r2;

@@ -4,36 +4,31 @@
 // (/root/reference/gaussian_renderer/__init__.py:1271-1282, train_internal.py:195).
 //
 // One CTA = one 16x16 tile (BLOCK_X/Y are observable through _C.get_block_XY and baked into the
-// reference's strip arithmetic, loss_distribution.py:2321-2330).  Each warp owns an 8x4 pixel
-// block so that warp votes can skip splats that miss the block.  Sorted splat ids are turned
-// into 48-byte packed records (3 x float4, built by k_count_tiles) staged in shared memory.
-//
-// Both kernels are bound by fp32 ALU / MUFU work over (pixel, splat) pairs, not by HBM: the
-// algorithmic traffic is 40 B per instance forward and 76 B backward against
-// 256 pair evaluations per instance.
-//
-// Backward reduction hierarchy (replaces the 9 global atomics per pixel per splat of the
-// classical design): lane -> warp by a 9-value transposing butterfly (14 shuffles instead of 45)
-// -> per-warp private shared-memory slots (no shared atomics: sm_100 has no native fp32 ATOMS.ADD)
-// -> one thread per splat sums the warps and issues ONE set of 9 global RED.ADD per (splat, tile).
+// reference's strip arithmetic, loss_distribution.py:2321-2330); each warp owns an 8x4 pixel block.
+// Both kernels are bound by instruction issue over (pixel, splat) pairs, not by HBM (ncu: issue slots
+// ~88 % busy, DRAM ~2 %; algorithmic traffic is only 40 B / 76 B per instance), so the
+// design minimises instructions per pair:
+//   * sorted splat ids are turned into 48-byte packed records (3 x float4, built by k_count_tiles) staged in
+//     shared memory together with an 8-bit "which 8x4 blocks can this splat reach" mask computed from the
+//     bounding box of its {alpha >= 1/255} ellipse; a warp ballots 32 masks at a time and only walks the
+//     splats that can touch its block (conservative: per-pixel results are unchanged);
+//   * the alpha < 1/255 test is done on the exponent (power < ln(1/(255 o)) - margin) so rejected pairs never
+//     reach MUFU.EX2; terminated pixels carry NaN coordinates so they drop out with no extra test;
+//   * backward reduction hierarchy (replaces the 9 global atomics per pixel per splat of the classical
+//     design): lane -> warp by a 9-value transposing butterfly (14 shuffles instead of 45) -> per-warp private
+//     shared-memory slots (no shared atomics: sm_100 has no native fp32 ATOMS.ADD) -> one thread per splat
+//     sums the warps and issues ONE set of global RED.ADD per (splat, tile).
 #include "common.cuh"
 
 #define BL_THREADS 256
+#define BL_WARPS (BL_THREADS / 32)
 #define FW_CHUNK 256
 #define BW_CHUNK 128
-#define BW_WARPS (BL_THREADS / 32)
 #define BW_STRIDE (BW_CHUNK + 1)
 
 #define ALPHA_MIN (1.0f / 255.0f)
 #define ALPHA_MAX 0.99f
 #define T_EPS 0.0001f
-// splats whose power is this far below ln(1/(255*opacity)) cannot reach alpha >= 1/255: skip exp()
-#define THR_MARGIN 0.02f
-
-GS_D float gs_alpha_of(float opacity, float power, float &G) {
-    G = __expf(power);
-    return fminf(ALPHA_MAX, opacity * G);
-}
 
 GS_D void pixel_of_thread(int tile, int gx, int &px, int &py) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -41,15 +36,30 @@ GS_D void pixel_of_thread(int tile, int gx, int &px, int &py) {
     py = (tile / gx) * GS_BLOCK_Y + (w >> 1) * 4 + (lane >> 3);
 }
 
+// bit w set <=> the splat's bounding box (centre m, half extents e) overlaps warp w's 8x4 pixel block
+GS_D uint32_t block_mask(float mx, float my, float ex, float ey, float X0, float Y0) {
+    if (ex < 0.f) return 0u;
+    const float xl = mx - ex - X0, xh = mx + ex - X0, yl = my - ey - Y0, yh = my + ey - Y0;
+    const uint32_t xm = ((xh >= 0.f && xl <= 7.f) ? 1u : 0u) | ((xh >= 8.f && xl <= 15.f) ? 2u : 0u);
+    uint32_t m = 0u;
+#pragma unroll
+    for (int wy = 0; wy < 4; wy++)
+        if (yh >= 4.f * wy && yl <= 4.f * wy + 3.f) m |= xm << (2 * wy);
+    return m;
+}
+
 __global__ void __launch_bounds__(BL_THREADS)
 k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restrict__ bg,
             const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
             const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
             uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats) {
-    __shared__ float4 s_r0[FW_CHUNK], s_r1[FW_CHUNK], s_r2[FW_CHUNK];
+    __shared__ float4 s_r0[FW_CHUNK], s_r1[FW_CHUNK];
+    __shared__ float2 s_gb[FW_CHUNK];
+    __shared__ uint8_t s_cull[FW_CHUNK];
     __shared__ unsigned long long s_stats[3];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
     const int tile = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int px, py;
     pixel_of_thread(tile, gx, px, py);
     const bool inside = px < W && py < H;
@@ -61,7 +71,9 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
     }
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
-    const float pxf = (float)px, pyf = (float)py;
+    const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
+    const float qnan = __int_as_float(0x7fc00000);
+    float pxf = inside ? (float)px : qnan, pyf = (float)py;  // NaN coordinates: the pixel never passes a test
     float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0, blended = 0, considered = 0;
     bool done = !inside;
@@ -71,35 +83,43 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
         if ((int)threadIdx.x < cnt) {
             const uint32_t g = ids[range.x + base + threadIdx.x];
             const float4 *r = rec + (size_t)3 * g;
-            s_r0[threadIdx.x] = __ldg(r); s_r1[threadIdx.x] = __ldg(r + 1); s_r2[threadIdx.x] = __ldg(r + 2);
+            const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+            s_r0[threadIdx.x] = a; s_r1[threadIdx.x] = b; s_gb[threadIdx.x] = make_float2(c.x, c.y);
+            s_cull[threadIdx.x] = (uint8_t)block_mask(a.x, a.y, c.z, c.w, X0, Y0);
         }
         __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;
-        for (int j = 0; j < cnt; j++) {
-            const float4 a = s_r0[j], b = s_r1[j];
-            const float dx = a.x - pxf, dy = a.y - pyf;
-            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-            bool ok = !done && power <= 0.f && power >= b.z - THR_MARGIN;
-            if (!__any_sync(0xffffffffu, ok)) continue;
-            if (ok) {
-                float G;
-                const float alpha = gs_alpha_of(b.y, power, G);
-                if (alpha >= ALPHA_MIN) {
-                    const float test_T = T * (1.f - alpha);
-                    if (test_T < T_EPS) {
-                        done = true;
-                        considered = (uint32_t)(base + j + 1);
-                    } else {
-                        const float4 c = s_r2[j];
-                        const float w = alpha * T;
-                        C0 += b.w * w; C1 += c.x * w; C2 += c.y * w;
-                        T = test_T;
-                        last = (uint32_t)(base + j + 1);
-                        blended++;
+        bool wdone = __all_sync(0xffffffffu, done);
+        for (int g0 = 0; g0 < cnt && !wdone; g0 += 32) {
+            const int jj = g0 + lane;
+            uint32_t cand = __ballot_sync(0xffffffffu, jj < cnt && ((s_cull[jj] >> warp) & 1));
+            while (cand) {
+                const int j = g0 + __ffs(cand) - 1;
+                cand &= cand - 1;
+                const float4 a = s_r0[j], b = s_r1[j];
+                const float dx = a.x - pxf, dy = a.y - pyf;
+                const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
+                const bool ok = power >= b.z;  // false for NaN (finished / outside pixels)
+                if (!__any_sync(0xffffffffu, ok)) continue;
+                if (ok && power <= 0.f) {
+                    const float alpha = fminf(ALPHA_MAX, b.y * __expf(power));
+                    if (alpha >= ALPHA_MIN) {
+                        const float test_T = T * (1.f - alpha);
+                        if (test_T < T_EPS) {
+                            done = true;
+                            pxf = qnan;
+                            considered = (uint32_t)(base + j + 1);
+                        } else {
+                            const float2 gb = s_gb[j];
+                            const float w = alpha * T;
+                            C0 += b.w * w; C1 += gb.x * w; C2 += gb.y * w;
+                            T = test_T;
+                            last = (uint32_t)(base + j + 1);
+                            blended++;
+                        }
                     }
                 }
+                if (__all_sync(0xffffffffu, done)) { wdone = true; break; }
             }
-            if (__all_sync(0xffffffffu, done)) break;  // reached by the whole warp (uniform vote above)
         }
     }
     if (inside) {
@@ -121,9 +141,7 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             v1 += __shfl_xor_sync(0xffffffffu, v1, o);
             v2 += __shfl_xor_sync(0xffffffffu, v2, o);
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&s_stats[0], v0); atomicAdd(&s_stats[1], v1); atomicAdd(&s_stats[2], v2);
-        }
+        if (lane == 0) { atomicAdd(&s_stats[0], v0); atomicAdd(&s_stats[1], v1); atomicAdd(&s_stats[2], v2); }
         __syncthreads();
         if (threadIdx.x < 3) atomicAdd(&stats[threadIdx.x], s_stats[threadIdx.x]);
     }
@@ -165,11 +183,13 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
             const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
             float *__restrict__ d_means2D, float *__restrict__ d_conic_opacity, float *__restrict__ d_rgb) {
-    __shared__ float4 s_r0[BW_CHUNK], s_r1[BW_CHUNK], s_r2[BW_CHUNK];
+    __shared__ float4 s_r0[BW_CHUNK], s_r1[BW_CHUNK];
+    __shared__ float2 s_gb[BW_CHUNK];
     __shared__ uint32_t s_id[BW_CHUNK];
-    __shared__ float s_acc[BW_WARPS][9][BW_STRIDE];
-    __shared__ uint32_t s_mask[BW_WARPS][BW_CHUNK / 32];
-    __shared__ uint32_t s_max[BW_WARPS];
+    __shared__ uint8_t s_cull[BW_CHUNK];
+    __shared__ float s_acc[BL_WARPS][9][BW_STRIDE];
+    __shared__ uint32_t s_mask[BL_WARPS][BW_CHUNK / 32];
+    __shared__ uint32_t s_max[BL_WARPS];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
     const int tile = blockIdx.x;
     if (!compute_locally[tile]) return;
@@ -180,6 +200,7 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
     const uint2 range = ranges[tile];
+    const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
     const float pxf = (float)px, pyf = (float)py;
     const float T_final = inside ? final_T[pix] : 0.f;
     const uint32_t last = inside ? n_contrib[pix] : 0u;
@@ -195,7 +216,8 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
     __syncthreads();
     uint32_t n_total = 0;
 #pragma unroll
-    for (int w = 0; w < BW_WARPS; w++) n_total = max(n_total, s_max[w]);
+    for (int w = 0; w < BL_WARPS; w++) n_total = max(n_total, s_max[w]);
+    const uint32_t wlast = m;  // deepest entry this warp's pixels reach
     float T = T_final, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
     const int n_chunks = ((int)n_total + BW_CHUNK - 1) / BW_CHUNK;
     for (int c = n_chunks - 1; c >= 0; c--) {
@@ -206,54 +228,70 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             const uint32_t g = ids[range.x + base + threadIdx.x];
             s_id[threadIdx.x] = g;
             const float4 *r = rec + (size_t)3 * g;
-            s_r0[threadIdx.x] = __ldg(r); s_r1[threadIdx.x] = __ldg(r + 1); s_r2[threadIdx.x] = __ldg(r + 2);
+            const float4 a = __ldg(r), b = __ldg(r + 1), cc = __ldg(r + 2);
+            s_r0[threadIdx.x] = a; s_r1[threadIdx.x] = b; s_gb[threadIdx.x] = make_float2(cc.x, cc.y);
+            s_cull[threadIdx.x] = (uint8_t)block_mask(a.x, a.y, cc.z, cc.w, X0, Y0);
         }
         uint32_t wmask = 0u;  // lane q holds bits [32q, 32q+32) of "this warp produced a partial for entry j"
         __syncthreads();
-        for (int j = cnt - 1; j >= 0; j--) {
-            const float4 a = s_r0[j], b = s_r1[j];
-            const float dx = a.x - pxf, dy = a.y - pyf;
-            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-            bool ok = ((uint32_t)(base + j) < last) && power <= 0.f && power >= b.z - THR_MARGIN;
-            if (!__any_sync(0xffffffffu, ok)) continue;
-            float G;
-            const float alpha = gs_alpha_of(b.y, power, G);
-            ok = ok && alpha >= ALPHA_MIN;
-            if (!__any_sync(0xffffffffu, ok)) continue;
-            float v[9];
+        if ((uint32_t)base < wlast) {
+            for (int g0 = (cnt - 1) & ~31; g0 >= 0; g0 -= 32) {
+                const int jj = g0 + lane;
+                uint32_t cand = __ballot_sync(0xffffffffu, jj < cnt && ((s_cull[jj] >> warp) & 1));
+                uint32_t mybits = 0u;
+                while (cand) {
+                    const int b31 = 31 - __clz(cand);
+                    const int j = g0 + b31;
+                    cand &= ~(1u << b31);
+                    const float4 a = s_r0[j], b = s_r1[j];
+                    const float dx = a.x - pxf, dy = a.y - pyf;
+                    const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
+                    bool ok = ((uint32_t)(base + j) < last) && power >= b.z;
+                    if (!__any_sync(0xffffffffu, ok)) continue;
+                    const float G = __expf(power);
+                    const float alpha = fminf(ALPHA_MAX, b.y * G);
+                    ok = ok && power <= 0.f && alpha >= ALPHA_MIN;
+                    if (!__any_sync(0xffffffffu, ok)) continue;
+                    float v[9];
 #pragma unroll
-            for (int q = 0; q < 9; q++) v[q] = 0.f;
-            if (ok) {
-                const float4 cc = s_r2[j];
-                const float col0 = b.w, col1 = cc.x, col2 = cc.y;
-                T = T / (1.f - alpha);
-                const float dchannel_dcolor = alpha * T;
-                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                lc0 = col0; lc1 = col1; lc2 = col2;
-                float dL_dalpha = (col0 - acc0) * dp0 + (col1 - acc1) * dp1 + (col2 - acc2) * dp2;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-                const float dL_dG = b.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * a.z - gdy * a.w;
-                const float dG_ddely = -gdy * b.x - gdx * a.w;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
-                v[6] = dchannel_dcolor * dp0;
-                v[7] = dchannel_dcolor * dp1;
-                v[8] = dchannel_dcolor * dp2;
+                    for (int q = 0; q < 9; q++) v[q] = 0.f;
+                    if (ok) {
+                        const float2 gb = s_gb[j];
+                        const float col0 = b.w, col1 = gb.x, col2 = gb.y;
+                        const float one_m = 1.f - alpha;
+                        const float inv = __fdividef(1.f, one_m);
+                        T = T * inv;
+                        const float dchannel_dcolor = alpha * T;
+                        acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                        acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                        acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                        lc0 = col0; lc1 = col1; lc2 = col2;
+                        float dL_dalpha = (col0 - acc0) * dp0 + (col1 - acc1) * dp1 + (col2 - acc2) * dp2;
+                        dL_dalpha *= T;
+                        last_alpha = alpha;
+                        dL_dalpha -= (T_final * inv) * bgdot;
+                        const float dL_dG = b.y * dL_dalpha;
+                        const float gdx = G * dx, gdy = G * dy;
+                        // A = -2a', B = -b', C = -2c'
+                        const float dG_ddelx = 2.f * gdx * a.z + gdy * a.w;
+                        const float dG_ddely = 2.f * gdy * b.x + gdx * a.w;
+                        v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                        v[1] = dL_dG * dG_ddely * ddely_dy;
+                        v[2] = -0.5f * gdx * dx * dL_dG;
+                        v[3] = -gdx * dy * dL_dG;
+                        v[4] = -0.5f * gdy * dy * dL_dG;
+                        v[5] = G * dL_dalpha;
+                        v[6] = dchannel_dcolor * dp0;
+                        v[7] = dchannel_dcolor * dp1;
+                        v[8] = dchannel_dcolor * dp2;
+                    }
+                    warp_reduce9(v, lane);
+                    if ((lane & 3) == 0) s_acc[warp][lane >> 2][j] = v[0];
+                    if (lane == 1) s_acc[warp][8][j] = v[8];
+                    mybits |= 1u << b31;
+                }
+                if (lane == (g0 >> 5)) wmask = mybits;
             }
-            warp_reduce9(v, lane);
-            if ((lane & 3) == 0) s_acc[warp][lane >> 2][j] = v[0];
-            if (lane == 1) s_acc[warp][8][j] = v[8];
-            if (lane == (j >> 5)) wmask |= 1u << (j & 31);
         }
         if (lane < BW_CHUNK / 32) s_mask[warp][lane] = wmask;
         __syncthreads();
@@ -264,7 +302,7 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             for (int q = 0; q < 9; q++) s[q] = 0.f;
             bool any = false;
 #pragma unroll
-            for (int w = 0; w < BW_WARPS; w++) {
+            for (int w = 0; w < BL_WARPS; w++) {
                 if ((s_mask[w][j >> 5] >> (j & 31)) & 1u) {
                     any = true;
 #pragma unroll
