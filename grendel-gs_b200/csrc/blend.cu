@@ -30,6 +30,13 @@
 #define ALPHA_MAX 0.99f
 #define T_EPS 0.0001f
 
+// exp(x) for x <= 0 as one FMUL + MUFU.EX2 (results below 2^-126 flush to 0: far under the 1/255 alpha floor)
+GS_D float gs_exp_neg(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 GS_D void pixel_of_thread(int tile, int gx, int &px, int &py) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     px = (tile % gx) * GS_BLOCK_X + (w & 1) * 8 + (lane & 7);
@@ -101,7 +108,7 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
                 const bool ok = power >= b.z;  // false for NaN (finished / outside pixels)
                 if (!__any_sync(0xffffffffu, ok)) continue;
                 if (ok && power <= 0.f) {
-                    const float alpha = fminf(ALPHA_MAX, b.y * __expf(power));
+                    const float alpha = fminf(ALPHA_MAX, b.y * gs_exp_neg(power));
                     if (alpha >= ALPHA_MIN) {
                         const float test_T = T * (1.f - alpha);
                         if (test_T < T_EPS) {
@@ -248,42 +255,30 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
                     const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
                     bool ok = ((uint32_t)(base + j) < last) && power >= b.z;
                     if (!__any_sync(0xffffffffu, ok)) continue;
-                    const float G = __expf(power);
+                    const float G = gs_exp_neg(power);
                     const float alpha = fminf(ALPHA_MAX, b.y * G);
                     ok = ok && power <= 0.f && alpha >= ALPHA_MIN;
                     if (!__any_sync(0xffffffffu, ok)) continue;
+                    // Per-pixel weight m = dL/dG * G; the per-splat gradients are its moments over the pixels
+                    // (S0, Sx, Sy, Sxx, Sxy, Syy) plus three colour sums; they are combined with the splat's
+                    // constants once per (splat, tile) in the flush below.
                     float v[9];
-#pragma unroll
-                    for (int q = 0; q < 9; q++) v[q] = 0.f;
-                    if (ok) {
+                    {
                         const float2 gb = s_gb[j];
-                        const float col0 = b.w, col1 = gb.x, col2 = gb.y;
                         const float one_m = 1.f - alpha;
                         const float inv = __fdividef(1.f, one_m);
-                        T = T * inv;
-                        const float dchannel_dcolor = alpha * T;
-                        acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                        acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                        acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                        lc0 = col0; lc1 = col1; lc2 = col2;
-                        float dL_dalpha = (col0 - acc0) * dp0 + (col1 - acc1) * dp1 + (col2 - acc2) * dp2;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha -= (T_final * inv) * bgdot;
-                        const float dL_dG = b.y * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        // A = -2a', B = -b', C = -2c'
-                        const float dG_ddelx = 2.f * gdx * a.z + gdy * a.w;
-                        const float dG_ddely = 2.f * gdy * b.x + gdx * a.w;
-                        v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                        v[1] = dL_dG * dG_ddely * ddely_dy;
-                        v[2] = -0.5f * gdx * dx * dL_dG;
-                        v[3] = -gdx * dy * dL_dG;
-                        v[4] = -0.5f * gdy * dy * dL_dG;
-                        v[5] = G * dL_dalpha;
-                        v[6] = dchannel_dcolor * dp0;
-                        v[7] = dchannel_dcolor * dp1;
-                        v[8] = dchannel_dcolor * dp2;
+                        const float Tn = T * inv;
+                        const float n0 = acc0 + last_alpha * (lc0 - acc0);
+                        const float n1 = acc1 + last_alpha * (lc1 - acc1);
+                        const float n2 = acc2 + last_alpha * (lc2 - acc2);
+                        float dL_dalpha = (b.w - n0) * dp0 + (gb.x - n1) * dp1 + (gb.y - n2) * dp2;
+                        dL_dalpha = dL_dalpha * Tn - (T_final * inv) * bgdot;
+                        const float mw = ok ? b.y * dL_dalpha * G : 0.f;
+                        const float dch = ok ? alpha * Tn : 0.f;
+                        if (ok) { T = Tn; acc0 = n0; acc1 = n1; acc2 = n2; lc0 = b.w; lc1 = gb.x; lc2 = gb.y; last_alpha = alpha; }
+                        const float mx_ = mw * dx, my_ = mw * dy;
+                        v[0] = mx_; v[1] = my_; v[2] = mx_ * dx; v[3] = mx_ * dy; v[4] = my_ * dy; v[5] = mw;
+                        v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
                     }
                     warp_reduce9(v, lane);
                     if ((lane & 3) == 0) s_acc[warp][lane >> 2][j] = v[0];
@@ -311,12 +306,14 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             }
             if (any) {
                 const uint32_t g = s_id[j];
-                atomicAdd(d_means2D + 2 * (size_t)g, s[0]);
-                atomicAdd(d_means2D + 2 * (size_t)g + 1, s[1]);
-                atomicAdd(d_conic_opacity + 4 * (size_t)g, s[2]);
-                atomicAdd(d_conic_opacity + 4 * (size_t)g + 1, s[3]);
-                atomicAdd(d_conic_opacity + 4 * (size_t)g + 2, s[4]);
-                atomicAdd(d_conic_opacity + 4 * (size_t)g + 3, s[5]);
+                const float4 a = s_r0[j], b = s_r1[j];  // (mx,my,a',b') (c',opacity,thr,red); A=-2a' B=-b' C=-2c'
+                // d power/d mean = (2a'dx + b'dy, 2c'dy + b'dx); dL/dmeans2D is per NDC unit: * (W/2, H/2)
+                atomicAdd(d_means2D + 2 * (size_t)g, (2.f * a.z * s[0] + a.w * s[1]) * ddelx_dx);
+                atomicAdd(d_means2D + 2 * (size_t)g + 1, (2.f * b.x * s[1] + a.w * s[0]) * ddely_dy);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g, -0.5f * s[2]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 1, -s[3]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 2, -0.5f * s[4]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 3, __fdividef(s[5], b.y));
                 atomicAdd(d_rgb + 3 * (size_t)g, s[6]);
                 atomicAdd(d_rgb + 3 * (size_t)g + 1, s[7]);
                 atomicAdd(d_rgb + 3 * (size_t)g + 2, s[8]);

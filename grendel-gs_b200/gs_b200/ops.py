@@ -154,6 +154,66 @@ def preprocess_gaussians(means3D, scales, rotations, shs, opacities, raster_sett
     return _PreprocessGaussians.apply(means3D, scales, rotations, shs, opacities, raster_settings)
 
 
+class _PreprocessGaussiansRaw(torch.autograd.Function):
+    """preprocess_gaussians with the GaussianModel activations fused in (gs_preprocess_*_raw)."""
+
+    @staticmethod
+    def forward(ctx, xyz, f_dc, f_rest, scaling, rotation, opacity, rs):
+        xyz, f_dc, f_rest = _f32c(xyz, "_xyz"), _f32c(f_dc, "_features_dc"), _f32c(f_rest, "_features_rest")
+        scaling, rotation, opacity = _f32c(scaling, "_scaling"), _f32c(rotation, "_rotation"), _f32c(opacity, "_opacity")
+        P = xyz.shape[0]
+        if tuple(f_dc.shape) != (P, 1, 3) or tuple(f_rest.shape) != (P, 15, 3):
+            raise ValueError("features must be (P,1,3) and (P,15,3) (scene/gaussian_model.py:219-228)")
+        if tuple(xyz.shape) != (P, 3) or tuple(scaling.shape) != (P, 3) or tuple(rotation.shape) != (P, 4) \
+                or opacity.numel() != P:
+            raise ValueError("inconsistent Gaussian parameter shapes")
+        dev = xyz.device
+        vm, pm, cp = _f32c(rs.viewmatrix, "viewmatrix"), _f32c(rs.projmatrix, "projmatrix"), _f32c(rs.campos, "campos")
+        means2D = torch.empty((P, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((P,), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        conic_opacity = torch.empty((P, 4), dtype=torch.float32, device=dev)
+        rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        clamped = torch.empty((P,), dtype=torch.uint8, device=dev)
+        _lib.call("gs_preprocess_forward_raw", P, int(rs.sh_degree), xyz.data_ptr(), f_dc.data_ptr(), f_rest.data_ptr(),
+                  scaling.data_ptr(), float(rs.scale_modifier), rotation.data_ptr(), opacity.data_ptr(), vm.data_ptr(),
+                  pm.data_ptr(), cp.data_ptr(), int(rs.image_width), int(rs.image_height), float(rs.tanfovx),
+                  float(rs.tanfovy), means2D.data_ptr(), depths.data_ptr(), radii.data_ptr(), conic_opacity.data_ptr(),
+                  rgb.data_ptr(), clamped.data_ptr(), _stream())
+        ctx.rs = rs
+        ctx.cam = (vm, pm, cp)
+        ctx.save_for_backward(xyz, f_dc, f_rest, scaling, rotation, opacity, radii, clamped)
+        ctx.mark_non_differentiable(radii, depths)
+        return means2D, rgb, conic_opacity, radii, depths
+
+    @staticmethod
+    def backward(ctx, g_means2D, g_rgb, g_conic_opacity, _g_radii, _g_depths):
+        xyz, f_dc, f_rest, scaling, rotation, opacity, radii, clamped = ctx.saved_tensors
+        rs = ctx.rs
+        vm, pm, cp = ctx.cam
+        P = xyz.shape[0]
+        dev = xyz.device
+
+        def z(g, shape):
+            return torch.zeros(shape, dtype=torch.float32, device=dev) if g is None else _f32c(g, "grad")
+
+        g_means2D, g_rgb, g_conic_opacity = z(g_means2D, (P, 2)), z(g_rgb, (P, 3)), z(g_conic_opacity, (P, 4))
+        d = [torch.empty_like(t) for t in (xyz, f_dc, f_rest, scaling, rotation, opacity)]
+        _lib.call("gs_preprocess_backward_raw", P, int(rs.sh_degree), xyz.data_ptr(), f_dc.data_ptr(), f_rest.data_ptr(),
+                  scaling.data_ptr(), float(rs.scale_modifier), rotation.data_ptr(), opacity.data_ptr(), vm.data_ptr(),
+                  pm.data_ptr(), cp.data_ptr(), int(rs.image_width), int(rs.image_height), float(rs.tanfovx),
+                  float(rs.tanfovy), radii.data_ptr(), clamped.data_ptr(), g_means2D.data_ptr(),
+                  g_conic_opacity.data_ptr(), g_rgb.data_ptr(), d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(),
+                  d[3].data_ptr(), d[4].data_ptr(), d[5].data_ptr(), _stream())
+        return d[0], d[1], d[2], d[3], d[4], d[5], None
+
+
+def preprocess_gaussians_raw(xyz, features_dc, features_rest, scaling, rotation, opacity, raster_settings):
+    """Same outputs as preprocess_gaussians, from the six RAW GaussianModel parameters
+    (scene/gaussian_model.py:219-228); the activations of :109-129 run inside the kernel."""
+    return _PreprocessGaussiansRaw.apply(xyz, features_dc, features_rest, scaling, rotation, opacity, raster_settings)
+
+
 def _tiles(rs):
     return (int(rs.image_height) + BLOCK_Y - 1) // BLOCK_Y, (int(rs.image_width) + BLOCK_X - 1) // BLOCK_X
 

@@ -112,11 +112,13 @@ class Trainer:
     their strip owners through exchange.exchange (skipped when W == 1, like gaussian_renderer/__init__.py:968).
     """
 
-    def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None):
+    def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None,
+                 fused_activations=True):
         from . import exchange as _ex
         self._ex = _ex
         self.device, self.rank, self.world, self.group = device, rank, world, group
         self.lambda_dssim = lambda_dssim
+        self.fused_activations = fused_activations
         n = scene["means3D"].shape[0]
         lo, hi = n * rank // world, n * (rank + 1) // world
         self.params = GaussianParams({k: v[lo:hi] for k, v in scene.items()}, device)
@@ -157,12 +159,18 @@ class Trainer:
         uids = [c.uid for c in self.dcams]
         strategies, _tasks = start_strategy(uids, self.history, self.world, self.rank)
         settings = [c.settings(p.active_sh_degree) for c in self.dcams]
-        xyz, scaling, rotation, feats, opacity = p.get_xyz, p.get_scaling, p.get_rotation, p.get_features, p.get_opacity
+        if not self.fused_activations:  # the reference's five activation kernels + cat (__init__.py:902-906)
+            xyz, scaling, rotation, feats, opacity = p.get_xyz, p.get_scaling, p.get_rotation, p.get_features, p.get_opacity
         collectors = [{} for _ in self.dcams]
         screen = []
         V = 0
         for k, rs in enumerate(settings):
-            out = ops_.preprocess_gaussians(xyz, scaling, rotation, feats, opacity, rs, {"stats_collector": collectors[k]})
+            if self.fused_activations:
+                out = ops_.preprocess_gaussians_raw(p._xyz, p._features_dc, p._features_rest, p._scaling, p._rotation,
+                                                    p._opacity, rs)
+            else:
+                out = ops_.preprocess_gaussians(xyz, scaling, rotation, feats, opacity, rs,
+                                                {"stats_collector": collectors[k]})
             out[0].retain_grad()
             screen.append(out)
         self.means2D = [s[0] for s in screen]

@@ -80,6 +80,27 @@ GS_API int gs_preprocess_backward(int P, int sh_degree, const float *means3D, co
                            const float *dL_dconic_opacity, const float *dL_drgb, float *dL_dmeans3D, float *dL_dscales,
                            float *dL_drotations, float *dL_dopacities, float *dL_dshs, void *stream);
 
+/* Fused-activation variants (SURVEY.md 8f "next" #3): take the six RAW GaussianModel parameters
+ * (/root/reference/scene/gaussian_model.py:219-228: _xyz (P,3), _features_dc (P,1,3), _features_rest (P,15,3),
+ * _scaling (P,3) log, _rotation (P,4) unnormalised, _opacity (P,1) logit), apply the activations of
+ * gaussian_model.py:109-129 (exp, normalize, sigmoid, cat) in registers, and return gradients for the raw
+ * tensors.  They replace the five torch activation kernels + torch.cat of
+ * gaussian_renderer/__init__.py:902-906 and their autograd backward. */
+GS_API int gs_preprocess_forward_raw(int P, int sh_degree, const float *xyz, const float *features_dc,
+                                     const float *features_rest, const float *scaling, float scale_modifier,
+                                     const float *rotation, const float *opacity, const float *viewmatrix,
+                                     const float *projmatrix, const float *campos, int image_width, int image_height,
+                                     float tanfovx, float tanfovy, float *means2D, float *depths, int32_t *radii,
+                                     float *conic_opacity, float *rgb, uint8_t *clamped, void *stream);
+GS_API int gs_preprocess_backward_raw(int P, int sh_degree, const float *xyz, const float *features_dc,
+                                      const float *features_rest, const float *scaling, float scale_modifier,
+                                      const float *rotation, const float *opacity, const float *viewmatrix,
+                                      const float *projmatrix, const float *campos, int image_width, int image_height,
+                                      float tanfovx, float tanfovy, const int32_t *radii, const uint8_t *clamped,
+                                      const float *dL_dmeans2D, const float *dL_dconic_opacity, const float *dL_drgb,
+                                      float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
+                                      float *dL_dscaling, float *dL_drotation, float *dL_dopacity, void *stream);
+
 /* _C.get_local2j_ids_bool -- /root/reference/gaussian_renderer/workload_division.py:721-744.
  * strategy: (world_size+1) int32 ascending flattened tile ids; out: (P, world_size) uint8/bool. */
 GS_API int gs_get_local2j_ids_bool(int P, int image_height, int image_width, int world_size, const float *means2D,

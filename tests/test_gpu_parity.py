@@ -236,3 +236,72 @@ def test_empty_and_degenerate_inputs():
     m2, rgb, co, radii, depths = r.preprocess_gaussians(e(0, 3), e(0, 3), e(0, 4), e(0, 16, 3), e(0, 1), {})
     img, *_ = r.render_gaussians(m2, co, rgb, depths, radii, None, None, {})
     assert img.shape == (3, 48, 64)
+
+
+def test_fused_activation_preprocess_matches_torch_activations(o32):
+    """gs_preprocess_*_raw == torch activations (exp / normalize / sigmoid / cat) followed by the plain operator."""
+    from gs_b200 import ops, pipeline
+    cam, sc = case(30003, 320, 200, seed=12)   # ragged tail: 30003 % 128 % 4 != 0 exercises the non-TMA path
+    params = pipeline.GaussianParams(sc, "cuda")
+    with torch.no_grad():
+        params._rotation.mul_(torch.empty(30003, 1, device="cuda").uniform_(0.5, 2.0))   # unnormalised quaternions
+    dcam = pipeline.DeviceCamera(cam, "cuda")
+    rs = dcam.settings(3)
+    a = ops.preprocess_gaussians(params.get_xyz, params.get_scaling, params.get_rotation, params.get_features,
+                                 params.get_opacity, rs)
+    rng = torch.Generator(device="cuda").manual_seed(0)
+    gm = torch.randn(a[0].shape, device="cuda", generator=rng)
+    gr = torch.randn(a[1].shape, device="cuda", generator=rng)
+    gc = torch.randn(a[2].shape, device="cuda", generator=rng)
+    (a[0] * gm).sum().add((a[1] * gr).sum()).add((a[2] * gc).sum()).backward()
+    ref_grads = [t.grad.clone() for t in params.raw_parameters()]
+    for t in params.raw_parameters():
+        t.grad = None
+    b = ops.preprocess_gaussians_raw(params._xyz, params._features_dc, params._features_rest, params._scaling,
+                                     params._rotation, params._opacity, rs)
+    (b[0] * gm).sum().add((b[1] * gr).sum()).add((b[2] * gc).sum()).backward()
+    same = (a[3] == b[3]).float().mean().item()
+    print(f"[parity] fused activations: radii identical for {same:.6f} of splats")
+    assert same >= 0.9999
+    keep = gu.npy(a[3] == b[3])
+    # exp and sigmoid reproduce torch bit for bit; normalize may differ in the last ulp, which ill-conditioned
+    # (needle-like) splats amplify in conic = adj(cov2D)/det -- hence a count-bounded comparison.
+    for x, y, name in ((a[0], b[0], "means2D"), (a[1], b[1], "rgb"), (a[2], b[2], "conic_opacity"), (a[4], b[4], "depths")):
+        frac, _ = gu.rel_report("fused.out." + name, gu.npy(y)[keep], gu.npy(x)[keep], rtol=1e-4, atol_scale=1e-6)
+        assert frac <= 1e-3, name
+    assert torch.equal(a[0][torch.as_tensor(keep, device="cuda")], b[0][torch.as_tensor(keep, device="cuda")])
+    for t, g, name in zip(params.raw_parameters(), ref_grads, ("xyz", "f_dc", "f_rest", "scaling", "rotation", "opacity")):
+        frac, _ = gu.rel_report("fused." + name, gu.npy(t.grad)[keep], gu.npy(g)[keep], rtol=1e-3, atol_scale=1e-4)
+        assert frac <= 1e-3, name
+
+
+def test_whole_step_parity_fused_path(o32):
+    """The Trainer's default (fused activations) step against the oracle, raw-parameter gradients included."""
+    from gs_b200 import pipeline
+    cam = syn.make_camera(400, 400)
+    sc = syn.make_scene(50000, 400, 400)
+    gt = syn.make_gt_image(400, 400)
+    ref = o32.train_step(sc, cam, gt)
+    tr = pipeline.Trainer(sc, [cam], [torch.from_numpy(gt).pin_memory()], torch.device("cuda", 0))
+    loss = tr.step(resident=False)
+    assert abs(loss - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    p = tr.params
+    frac, _ = gu.rel_report("fusedstep.xyz", gu.npy(p._xyz.grad), ref["grads"]["means3D"])
+    assert frac <= 5 * OUTLIER_FRAC
+    # chain rule through the activations, evaluated in numpy on the oracle's gradients
+    g_sc = ref["grads"]["scales"] * sc["scales"]
+    frac, _ = gu.rel_report("fusedstep.scaling", gu.npy(p._scaling.grad), g_sc)
+    assert frac <= 5 * OUTLIER_FRAC
+    op = sc["opacities"]
+    frac, _ = gu.rel_report("fusedstep.opacity", gu.npy(p._opacity.grad), ref["grads"]["opacities"] * op * (1 - op))
+    assert frac <= 5 * OUTLIER_FRAC
+    shg = ref["grads"]["shs"]
+    frac, _ = gu.rel_report("fusedstep.f_dc", gu.npy(p._features_dc.grad), shg[:, :1])
+    assert frac <= 5 * OUTLIER_FRAC
+    frac, _ = gu.rel_report("fusedstep.f_rest", gu.npy(p._features_rest.grad), shg[:, 1:])
+    assert frac <= 5 * OUTLIER_FRAC
+    q = sc["rotations"]
+    gq = ref["grads"]["rotations"]
+    g_rot = gq - q * (q * gq).sum(1, keepdims=True)   # |q| = 1
+    frac, _ = gu.rel_report("fusedstep.rotation", gu.npy(p._rotation.grad), g_rot)
+    assert frac <= 5 * OUTLIER_FRAC
