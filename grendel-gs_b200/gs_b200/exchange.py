@@ -80,9 +80,10 @@ def all_to_all_single(out, inp, out_splits, in_splits, group=None):
 def gather_counts(local_counts, group=None):
     """(B, W) int32 device tensor -> nested list cnt[i][k][j]; the step's one host sync."""
     W = dist.get_world_size(group)
-    allc = torch.empty((W,) + tuple(local_counts.shape), dtype=local_counts.dtype, device=local_counts.device)
-    dist.all_gather_into_tensor(allc, local_counts.contiguous(), group=group)
-    return allc.cpu().tolist()
+    flat = local_counts.contiguous().reshape(-1)
+    allc = torch.empty((W * flat.numel(),), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(allc, flat, group=group)
+    return allc.reshape((W,) + tuple(local_counts.shape)).cpu().tolist()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -1,0 +1,210 @@
+"""CPU tests of the host-side logic: workload division (single process) and the all-to-all layout
+over a real 2-rank gloo group (the N>1 path of bench.py / pipeline.Trainer, minus the CUDA kernels)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gs_b200 import division, exchange
+
+
+# ---------------------------------------------------------------------------------------------------
+# division (restates /root/reference/gaussian_renderer/workload_division.py:75-94,852-941)
+# ---------------------------------------------------------------------------------------------------
+def test_division_pos_uniform_matches_reference_example():
+    # TILE_Y=68 over 4 ranks -> [0,17,34,51,68]; 67 rows -> [0,16,33,50,67]
+    assert division.division_pos_heuristic(torch.ones(68), 4) == [0, 17, 34, 51, 68]
+    assert division.division_pos_heuristic(torch.ones(67), 4) == [0, 16, 33, 50, 67]
+
+
+def test_division_weighted_costs_shift_boundaries():
+    h = torch.ones(40)
+    h[:10] = 5.0  # top rows are expensive
+    pos = division.division_pos_heuristic(h, 2)
+    assert pos[0] == 0 and pos[-1] == 40 and pos[1] < 20
+
+
+@pytest.mark.parametrize("world,bsz,tile_y", [(1, 1, 68), (2, 1, 68), (4, 4, 68), (8, 8, 135), (4, 1, 67), (8, 2, 135), (2, 4, 25)])
+def test_start_strategy_partitions_every_row_exactly_once(world, bsz, tile_y):
+    uids = list(range(bsz))
+    hist = division.StrategyHistory(uids, tile_y, world)
+    per_rank = []
+    for rank in range(world):
+        strategies, tasks = division.start_strategy(uids, hist, world, rank)
+        per_rank.append((strategies, tasks))
+    s0, t0 = per_rank[0]
+    for strategies, tasks in per_rank:  # every rank derives the same plan
+        assert [s.division_pos for s in strategies] == [s.division_pos for s in s0]
+        assert tasks == t0
+    for k, s in enumerate(s0):
+        assert s.division_pos[0] == 0 and s.division_pos[-1] == tile_y
+        assert len(s.gpu_ids) == len(s.division_pos) - 1
+    covered = np.zeros((bsz, tile_y), int)
+    for gpu, tl in enumerate(t0):
+        assert tl, f"rank {gpu} got no work"
+        for (k, lo, hi) in tl:
+            covered[k, lo:hi] += 1
+    assert (covered == 1).all()
+    # ranks own contiguous runs of the concatenated rows, in rank order
+    flat = [(k * tile_y + lo, k * tile_y + hi) for tl in t0 for (k, lo, hi) in tl]
+    assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))
+
+
+def test_strategy_masks_and_pixel_rows():
+    hist = division.StrategyHistory([0], 68, 4)
+    strategies, _ = division.start_strategy([0], hist, 4, 2)
+    s = strategies[0]
+    assert s.rank == 2 and s.local_rows() == (34, 51)
+    m = s.get_compute_locally(120, "cpu")
+    assert m.shape == (68, 120) and m[34:51].all() and not m[:34].any() and not m[51:].any()
+    assert s.local_pixel_rows(1080) == (34 * 16, 51 * 16)
+    assert strategies[0].strategy_tensor(120, "cpu").tolist() == [0, 17 * 120, 34 * 120, 51 * 120, 68 * 120]
+    last = division.start_strategy([0], hist, 4, 3)[0][0]
+    assert last.local_pixel_rows(1080) == (51 * 16, 1080)  # last strip is clipped to the image
+
+
+def test_history_update_rebalances():
+    hist = division.StrategyHistory([7], 64, 2)
+    strategies, _ = division.start_strategy([7], hist, 2, 0)
+    assert strategies[0].division_pos == [0, 32, 64]
+    hist.update(strategies, [[30.0], [10.0]])  # rank 0 took 3x longer
+    s2, _ = division.start_strategy([7], hist, 2, 0)
+    assert s2[0].division_pos[1] < 32
+
+
+def test_local_sampling_gives_whole_images():
+    hist = division.StrategyHistory([0, 1, 2, 3], 30, 2)
+    strategies, tasks = division.start_strategy([0, 1, 2, 3], hist, 2, 1, local_sampling=True)
+    assert [s.gpu_ids for s in strategies] == [[0], [0], [1], [1]]
+    assert tasks[1] == [(2, 0, 30), (3, 0, 30)]
+
+
+def test_invalid_division_is_rejected():
+    with pytest.raises(ValueError):
+        division.DivisionStrategy(0, [0, 1], [0, 10], 20, 0)
+    with pytest.raises(ValueError):
+        division.DivisionStrategy(0, [0, 1], [0, 12, 12], 12, 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# exchange layout over gloo, world_size = 2 and 3
+# ---------------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_data(rank, B, P, world, gpu_ids):
+    g = torch.Generator().manual_seed(1000 + rank)
+    rows = [torch.rand((P, exchange.ROW), generator=g) + 10 * rank + 100 * k for k in range(B)]
+    masks = [torch.rand((P, len(gpu_ids[k])), generator=g) < 0.3 for k in range(B)]
+    return rows, masks
+
+
+def _worker(rank, world, port, B, P, tile_y, q):
+    try:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        uids = list(range(B))
+        hist = division.StrategyHistory(uids, tile_y, world)
+        strategies, _ = division.start_strategy(uids, hist, world, rank)
+        gpu_ids = [s.gpu_ids for s in strategies]
+        rows, masks = _rank_data(rank, B, P, world, gpu_ids)
+        local_counts = torch.zeros((B, world), dtype=torch.int32)
+        for k in range(B):
+            local_counts[k, torch.tensor(gpu_ids[k])] = masks[k].sum(0).to(torch.int32)
+        cnt = exchange.gather_counts(local_counts)
+        lay = exchange.Layout(cnt, rank, gpu_ids)
+        # torch emulation of gs_pack_rows
+        send = torch.full((lay.total_send, exchange.ROW), -1.0)
+        for k in range(B):
+            for c in range(len(gpu_ids[k])):
+                sel = rows[k][masks[k][:, c]]
+                send[lay.dst_off[k][c]:lay.dst_off[k][c] + sel.shape[0]] = sel
+        assert (send >= 0).all()
+        recv = torch.empty((lay.total_recv, exchange.ROW))
+        exchange.all_to_all_single(recv, send, lay.recv_splits, lay.send_splits)
+        # torch emulation of gs_unpack_rows + the expected answer recomputed from every source's seed
+        for k in range(B):
+            got = torch.cat([recv[o:o + l] for o, l in zip(lay.seg_off[k], lay.seg_len[k])]) if lay.n_recv[k] else recv[:0]
+            exp = []
+            for src in range(world):
+                r_src, m_src = _rank_data(src, B, P, world, gpu_ids)
+                if rank in gpu_ids[k]:
+                    exp.append(r_src[k][m_src[k][:, gpu_ids[k].index(rank)]])
+            exp = torch.cat(exp) if exp else recv[:0]
+            assert torch.equal(got, exp), f"camera {k}"
+        # backward: gradient rows travel the reverse route and are summed per local splat
+        grecv = torch.zeros((lay.total_recv, exchange.GROW))
+        for k in range(B):
+            n = lay.n_recv[k]
+            g = torch.arange(n, dtype=torch.float32)[:, None] + torch.arange(exchange.GROW)[None] * 0.001 + 1000 * rank + 10000 * k
+            o2 = 0
+            for o, l in zip(lay.seg_off[k], lay.seg_len[k]):
+                grecv[o:o + l] = g[o2:o2 + l]
+                o2 += l
+        gsend = torch.empty((lay.total_send, exchange.GROW))
+        exchange.all_to_all_single(gsend, grecv, lay.send_splits, lay.recv_splits)
+        for k in range(B):
+            acc = torch.zeros((P, exchange.GROW))
+            for c, dest in enumerate(gpu_ids[k]):
+                idx = masks[k][:, c].nonzero().squeeze(1)
+                acc[idx] += gsend[lay.dst_off[k][c]:lay.dst_off[k][c] + idx.numel()]
+                # what `dest` must have assigned to these rows: its camera-k rows from source `rank` start after
+                # the rows it received from lower ranks
+                before = sum(cnt[i][k][dest] for i in range(rank))
+                exp = (before + torch.arange(idx.numel(), dtype=torch.float32))[:, None] + torch.arange(exchange.GROW)[None] * 0.001 + 1000 * dest + 10000 * k
+                assert torch.allclose(gsend[lay.dst_off[k][c]:lay.dst_off[k][c] + idx.numel()], exp)
+            assert (acc[~masks[k].any(1)] == 0).all()
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.parametrize("world,B,tile_y", [(2, 1, 68), (2, 2, 25), (3, 4, 40)])
+def test_exchange_layout_over_gloo(world, B, tile_y):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, B, 257, tile_y, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_layout_is_consistent_without_a_group():
+    rng = np.random.default_rng(0)
+    W, B = 4, 3
+    gpu_ids = [[0, 1], [1, 2, 3], [3]]
+    cnt = np.zeros((W, B, W), int)
+    for i in range(W):
+        for k in range(B):
+            for j in gpu_ids[k]:
+                cnt[i, k, j] = rng.integers(0, 50)
+    cnt = cnt.tolist()
+    lays = [exchange.Layout(cnt, me, gpu_ids) for me in range(W)]
+    for a in range(W):
+        for b in range(W):
+            assert lays[a].send_splits[b] == lays[b].recv_splits[a]
+        assert lays[a].total_recv == sum(lays[a].n_recv)
+        # send offsets tile the send buffer without gaps
+        spans = sorted((lays[a].dst_off[k][c], cnt[a][k][j]) for k in range(B) for c, j in enumerate(gpu_ids[k]))
+        pos = 0
+        for off, n in spans:
+            assert off == pos or n == 0
+            pos = max(pos, off + n)
+        assert pos == lays[a].total_send
