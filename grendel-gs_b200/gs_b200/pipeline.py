@@ -147,9 +147,26 @@ class Trainer:
         self._h2d += h.numel()
         return h.to(self.device, non_blocking=True)
 
+    def _mark(self, name):
+        """GS_B200_TRACE=1: synchronise and accumulate wall-clock per phase (diagnostics only)."""
+        if not self._trace_on:
+            return
+        import time
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.trace[name] = self.trace.get(name, 0.0) + (now - self._t_last) * 1e3
+        self._t_last = now
+
     def step(self, resident=True):
         """One forward + loss + backward over the batch.  resident=False copies the GT strips from pinned host
         memory inside the step and reads the loss back (the end-to-end leg); returns the loss as a float then."""
+        import os as _os, time as _time
+        self._trace_on = _os.environ.get("GS_B200_TRACE") == "1"
+        if self._trace_on:
+            if not hasattr(self, "trace"):
+                self.trace = {}
+            torch.cuda.synchronize()
+            self._t_last = _time.perf_counter()
         ops_ = ops
         p = self.params
         for t in p.raw_parameters():
@@ -174,10 +191,12 @@ class Trainer:
             out[0].retain_grad()
             screen.append(out)
         self.means2D = [s[0] for s in screen]
+        self._mark("preprocess")
         if self.world > 1:
             redistributed, cnt = self._ex.exchange(screen, strategies, settings, self.world, self.rank, self.group)
         else:
             redistributed = screen
+        self._mark("exchange")
         loss_sum = None
         Vp = Pl = 0
         for k, st in enumerate(strategies):
@@ -194,7 +213,9 @@ class Trainer:
             loss_sum = loss if loss_sum is None else loss_sum + loss
             Vp += m2.shape[0]
             Pl += (y1 - y0) * self.W
+        self._mark("render+loss")
         loss_sum.backward()
+        self._mark("backward")
         self._collectors, self._strategies = collectors, strategies
         self._counts = dict(Vp=Vp, P_local=Pl, screen=screen)
         if resident:
