@@ -288,3 +288,298 @@ extern "C" int gs_scatter_grad_rows(int P, int ncols, const uint8_t *mask, const
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
+
+// ---- batched exchange: ALL cameras of a step in one launch per stage ------------------------------------
+// The per-camera calls above cost O(B) launches and Python round trips per step; with B = W = 8 that is the
+// scaling limiter, not NVLink (5-25 k splats per (src,dst) pair, latency dominated).
+// Here the flag stream is laid out [destination rank j][camera k][splat i]; ONE exclusive scan over it yields the
+// row of every (j,k,i) in the send buffer directly, because that order IS the all_to_all_single send layout
+// (per destination: cameras in batch order, splats in index order -- gaussian_renderer/__init__.py:590-607).
+#define XB 16   // max cameras per step
+#define XW 16   // max ranks
+#define XSEG 128
+
+struct XIn { const float *m2[XB]; const float *rgb[XB]; const float *co[XB]; const int32_t *rad[XB]; const float *dep[XB]; };
+struct XOut { float *m2[XB]; float *rgb[XB]; float *co[XB]; int32_t *rad[XB]; float *dep[XB]; };
+struct XRows { int16_t lo[XB * XW]; int16_t hi[XB * XW]; };
+struct XSegs { int32_t recv_start[XSEG]; int32_t dst_start[XSEG]; uint8_t cam[XSEG]; int n; };
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_xchg_flags(int B, int P, int Wr, int W, int H, XIn in, XRows rows, uint8_t *__restrict__ flags) {
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
+    if (i >= P) return;
+    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
+    const int r = in.rad[k][i];
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (r > 0) {
+        const float2 m = *reinterpret_cast<const float2 *>(in.m2[k] + 2 * i);
+        gs_get_rect(m.x, m.y, r, gx, gy, x0, y0, x1, y1);
+    }
+    for (int j = 0; j < Wr; j++) {
+        const int lo = rows.lo[k * XW + j], hi = rows.hi[k * XW + j];
+        const bool hit = x1 > x0 && max(y0, lo) < min(y1, hi);
+        flags[((size_t)j * B + k) * P + i] = hit ? 1 : 0;
+    }
+}
+
+struct FlagToInt {
+    const uint8_t *f;
+    __host__ __device__ int32_t operator()(int e) const { return f[e]; }
+};
+
+__global__ void k_xchg_counts(int n_cols, int P, const uint8_t *__restrict__ flags, const int32_t *__restrict__ gpos,
+                              int32_t *__restrict__ counts) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;  // column = j*B + k
+    if (c >= n_cols) return;
+    const size_t last = (size_t)(c + 1) * P - 1;
+    const int32_t end = gpos[last] + (flags[last] ? 1 : 0);
+    counts[c] = end - gpos[(size_t)c * P];
+}
+
+extern "C" size_t gs_xchg_temp_bytes(int B, int P, int W) {
+    size_t b = 0;
+    const long long n = (long long)(B > 0 ? B : 1) * (P > 0 ? P : 1) * (W > 0 ? W : 1);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n);
+    return align_up(b, 256) + 256;
+}
+
+static int fill_in(XIn &in, int B, const void *const *m2, const void *const *rgb, const void *const *co,
+                   const void *const *rad, const void *const *dep) {
+    for (int k = 0; k < XB; k++) {
+        in.m2[k] = (k < B && m2) ? (const float *)m2[k] : nullptr;
+        in.rgb[k] = (k < B && rgb) ? (const float *)rgb[k] : nullptr;
+        in.co[k] = (k < B && co) ? (const float *)co[k] : nullptr;
+        in.rad[k] = (k < B && rad) ? (const int32_t *)rad[k] : nullptr;
+        in.dep[k] = (k < B && dep) ? (const float *)dep[k] : nullptr;
+    }
+    return GS_OK;
+}
+
+// row_lo_host/row_hi_host: (B*W) HOST ints, tile-row range [lo,hi) of camera k owned by rank j (lo>=hi: none).
+// flags: (W*B*P) uint8, gpos: (W*B*P) int32, counts: (W*B) int32 laid out [j][k].
+extern "C" int gs_xchg_route(int B, int P, int W, int image_height, int image_width,
+                             const void *const *means2D_ptrs_host, const void *const *radii_ptrs_host,
+                             const int32_t *row_lo_host, const int32_t *row_hi_host, uint8_t *flags, int32_t *gpos,
+                             int32_t *counts, void *temp, size_t temp_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GS_REQUIRE(B > 0 && B <= XB && W > 0 && W <= XW && P >= 0, "sizes (<= 16 cameras, <= 16 ranks)");
+    GS_REQUIRE(counts != nullptr, "counts");
+    if (P == 0) {
+        GS_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B * W, stream));
+        return GS_OK;
+    }
+    GS_REQUIRE((long long)B * P * W < (1ll << 31), "B*P*W overflows int32");
+    GS_REQUIRE(means2D_ptrs_host && radii_ptrs_host && row_lo_host && row_hi_host && flags && gpos && temp, "null pointer");
+    XIn in;
+    fill_in(in, B, means2D_ptrs_host, nullptr, nullptr, radii_ptrs_host, nullptr);
+    XRows rows;
+    for (int k = 0; k < XB; k++)
+        for (int j = 0; j < XW; j++) {
+            const bool v = k < B && j < W;
+            rows.lo[k * XW + j] = v ? (int16_t)row_lo_host[k * W + j] : 0;
+            rows.hi[k * XW + j] = v ? (int16_t)row_hi_host[k * W + j] : 0;
+        }
+    {
+        GsStageTimer timer(GS_STAGE_LOCAL2J, stream);
+        dim3 grid((P + DT_THREADS - 1) / DT_THREADS, B);
+        k_xchg_flags<<<grid, DT_THREADS, 0, stream>>>(B, P, W, image_width, image_height, in, rows, flags);
+        GS_LAUNCH_CHECK();
+    }
+    GsStageTimer timer(GS_STAGE_PACK, stream);
+    const int n = B * P * W;
+    cub::CountingInputIterator<int> idx(0);
+    cub::TransformInputIterator<int32_t, FlagToInt, cub::CountingInputIterator<int>> it(idx, FlagToInt{flags});
+    GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, gpos, n, stream));
+    k_xchg_counts<<<(B * W + 63) / 64, 64, 0, stream>>>(B * W, P, flags, gpos, counts);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_xchg_pack(int B, int P, int Wr, XIn in, const uint8_t *__restrict__ flags, const int32_t *__restrict__ gpos,
+            float *__restrict__ out) {
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
+    if (i >= P) return;
+    bool any = false;
+    for (int j = 0; j < Wr; j++) any |= flags[((size_t)j * B + k) * P + i] != 0;
+    if (!any) return;
+    const float2 m = *reinterpret_cast<const float2 *>(in.m2[k] + 2 * i);
+    const float4 co = *reinterpret_cast<const float4 *>(in.co[k] + 4 * i);
+    const float r0 = in.rgb[k][3 * i], r1 = in.rgb[k][3 * i + 1], r2 = in.rgb[k][3 * i + 2];
+    const float rad = (float)in.rad[k][i], dep = in.dep[k][i];
+    for (int j = 0; j < Wr; j++) {
+        const size_t e = ((size_t)j * B + k) * P + i;
+        if (!flags[e]) continue;
+        float *o = out + (size_t)gpos[e] * ROW_FLOATS;
+        o[0] = m.x; o[1] = m.y; o[2] = r0; o[3] = r1; o[4] = r2;
+        o[5] = co.x; o[6] = co.y; o[7] = co.z; o[8] = co.w; o[9] = rad; o[10] = dep;
+    }
+}
+
+extern "C" int gs_xchg_pack(int B, int P, int W, const uint8_t *flags, const int32_t *gpos,
+                            const void *const *means2D_ptrs_host, const void *const *rgb_ptrs_host,
+                            const void *const *conic_opacity_ptrs_host, const void *const *radii_ptrs_host,
+                            const void *const *depths_ptrs_host, float *send_rows, void *stream) {
+    GS_REQUIRE(B > 0 && B <= XB && W > 0 && W <= XW && P >= 0, "sizes");
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(flags && gpos && means2D_ptrs_host && rgb_ptrs_host && conic_opacity_ptrs_host && radii_ptrs_host &&
+                   depths_ptrs_host && send_rows, "null pointer");
+    XIn in;
+    fill_in(in, B, means2D_ptrs_host, rgb_ptrs_host, conic_opacity_ptrs_host, radii_ptrs_host, depths_ptrs_host);
+    GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
+    dim3 grid((P + DT_THREADS - 1) / DT_THREADS, B);
+    k_xchg_pack<<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(B, P, W, in, flags, gpos, send_rows);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+__device__ __forceinline__ int xseg_find(const XSegs &s, int r) {
+    int lo = 0, hi = s.n - 1;  // last segment with recv_start <= r (empty segments share a start; any is fine
+    while (lo < hi) {          // as long as r falls inside it, so prefer the LAST one that starts at or before r)
+        const int mid = (lo + hi + 1) >> 1;
+        if (s.recv_start[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_xchg_unpack(int total, XSegs segs, const float *__restrict__ rows, XOut out) {
+    const int r = blockIdx.x * DT_THREADS + threadIdx.x;
+    if (r >= total) return;
+    const int s = xseg_find(segs, r);
+    const int k = segs.cam[s], i = segs.dst_start[s] + (r - segs.recv_start[s]);
+    const float *q = rows + (size_t)r * ROW_FLOATS;
+    out.m2[k][2 * i] = q[0]; out.m2[k][2 * i + 1] = q[1];
+    out.rgb[k][3 * i] = q[2]; out.rgb[k][3 * i + 1] = q[3]; out.rgb[k][3 * i + 2] = q[4];
+    *reinterpret_cast<float4 *>(out.co[k] + 4 * i) = make_float4(q[5], q[6], q[7], q[8]);
+    out.rad[k][i] = (int32_t)q[9];
+    out.dep[k][i] = q[10];
+}
+
+static int fill_segs(XSegs &s, int nseg, const int32_t *recv_start, const int32_t *seg_len, const int32_t *cam,
+                     const int32_t *dst_start) {
+    // keep only non-empty segments so that the binary search over recv_start is unambiguous
+    GS_REQUIRE(nseg >= 0 && recv_start && seg_len && cam && dst_start, "segments");
+    s.n = 0;
+    for (int q = 0; q < nseg; q++) {
+        if (seg_len[q] <= 0) continue;
+        GS_REQUIRE(s.n < XSEG, "too many (source, camera) segments (max 128)");
+        s.recv_start[s.n] = recv_start[q];
+        s.dst_start[s.n] = dst_start[q];
+        s.cam[s.n] = (uint8_t)cam[q];
+        s.n++;
+    }
+    for (int q = s.n; q < XSEG; q++) { s.recv_start[q] = 0x7fffffff; s.dst_start[q] = 0; s.cam[q] = 0; }
+    return GS_OK;
+}
+
+// Segments (source rank i, camera k) of the recv buffer, in recv order: first row, length, camera, first row
+// inside camera k's output tensors.  All four are HOST int32 arrays of length nseg.
+extern "C" int gs_xchg_unpack(int nseg, const int32_t *seg_recv_start_host, const int32_t *seg_len_host,
+                              const int32_t *seg_cam_host, const int32_t *seg_dst_start_host, int total_rows,
+                              const float *recv_rows, int B, void *const *means2D_ptrs_host, void *const *rgb_ptrs_host,
+                              void *const *conic_opacity_ptrs_host, void *const *radii_ptrs_host,
+                              void *const *depths_ptrs_host, void *stream) {
+    GS_REQUIRE(B > 0 && B <= XB && total_rows >= 0, "sizes");
+    if (total_rows == 0) return GS_OK;
+    XSegs s;
+    int rc = fill_segs(s, nseg, seg_recv_start_host, seg_len_host, seg_cam_host, seg_dst_start_host);
+    if (rc != GS_OK) return rc;
+    GS_REQUIRE(recv_rows && means2D_ptrs_host && rgb_ptrs_host && conic_opacity_ptrs_host && radii_ptrs_host &&
+                   depths_ptrs_host, "null pointer");
+    XOut out;
+    for (int k = 0; k < XB; k++) {
+        out.m2[k] = k < B ? (float *)means2D_ptrs_host[k] : nullptr;
+        out.rgb[k] = k < B ? (float *)rgb_ptrs_host[k] : nullptr;
+        out.co[k] = k < B ? (float *)conic_opacity_ptrs_host[k] : nullptr;
+        out.rad[k] = k < B ? (int32_t *)radii_ptrs_host[k] : nullptr;
+        out.dep[k] = k < B ? (float *)depths_ptrs_host[k] : nullptr;
+    }
+    GsStageTimer timer(GS_STAGE_UNPACK, (cudaStream_t)stream);
+    k_xchg_unpack<<<(total_rows + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(total_rows, s,
+                                                                                                       recv_rows, out);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+// backward of unpack: per-camera gradients -> 9-float rows in recv order (a camera without gradient: NULL -> zeros)
+__global__ void __launch_bounds__(DT_THREADS)
+k_xchg_pack_grad(int total, XSegs segs, XIn g, float *__restrict__ rows) {
+    const int r = blockIdx.x * DT_THREADS + threadIdx.x;
+    if (r >= total) return;
+    const int s = xseg_find(segs, r);
+    const int k = segs.cam[s], i = segs.dst_start[s] + (r - segs.recv_start[s]);
+    float *q = rows + (size_t)r * GRAD_FLOATS;
+    float v[GRAD_FLOATS];
+#pragma unroll
+    for (int t = 0; t < GRAD_FLOATS; t++) v[t] = 0.f;
+    if (g.m2[k]) { v[0] = g.m2[k][2 * i]; v[1] = g.m2[k][2 * i + 1]; }
+    if (g.rgb[k]) { v[2] = g.rgb[k][3 * i]; v[3] = g.rgb[k][3 * i + 1]; v[4] = g.rgb[k][3 * i + 2]; }
+    if (g.co[k]) {
+        const float4 c = *reinterpret_cast<const float4 *>(g.co[k] + 4 * i);
+        v[5] = c.x; v[6] = c.y; v[7] = c.z; v[8] = c.w;
+    }
+#pragma unroll
+    for (int t = 0; t < GRAD_FLOATS; t++) q[t] = v[t];
+}
+
+extern "C" int gs_xchg_pack_grad(int nseg, const int32_t *seg_recv_start_host, const int32_t *seg_len_host,
+                                 const int32_t *seg_cam_host, const int32_t *seg_dst_start_host, int total_rows, int B,
+                                 const void *const *d_means2D_ptrs_host, const void *const *d_rgb_ptrs_host,
+                                 const void *const *d_conic_opacity_ptrs_host, float *grad_rows, void *stream) {
+    GS_REQUIRE(B > 0 && B <= XB && total_rows >= 0, "sizes");
+    if (total_rows == 0) return GS_OK;
+    XSegs s;
+    int rc = fill_segs(s, nseg, seg_recv_start_host, seg_len_host, seg_cam_host, seg_dst_start_host);
+    if (rc != GS_OK) return rc;
+    GS_REQUIRE(grad_rows && d_means2D_ptrs_host && d_rgb_ptrs_host && d_conic_opacity_ptrs_host, "null pointer");
+    XIn g;
+    fill_in(g, B, d_means2D_ptrs_host, d_rgb_ptrs_host, d_conic_opacity_ptrs_host, nullptr, nullptr);
+    GsStageTimer timer(GS_STAGE_UNPACK, (cudaStream_t)stream);
+    k_xchg_pack_grad<<<(total_rows + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(total_rows, s,
+                                                                                                          g, grad_rows);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+// backward of pack: every (camera, local splat) sums the gradient rows returned by the ranks it was sent to
+__global__ void __launch_bounds__(DT_THREADS)
+k_xchg_scatter_grad(int B, int P, int Wr, const uint8_t *__restrict__ flags, const int32_t *__restrict__ gpos,
+                    const float *__restrict__ rows, XOut d) {
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
+    if (i >= P) return;
+    float a[GRAD_FLOATS];
+#pragma unroll
+    for (int q = 0; q < GRAD_FLOATS; q++) a[q] = 0.f;
+    for (int j = 0; j < Wr; j++) {
+        const size_t e = ((size_t)j * B + k) * P + i;
+        if (!flags[e]) continue;
+        const float *r = rows + (size_t)gpos[e] * GRAD_FLOATS;
+#pragma unroll
+        for (int q = 0; q < GRAD_FLOATS; q++) a[q] += r[q];
+    }
+    d.m2[k][2 * i] = a[0]; d.m2[k][2 * i + 1] = a[1];
+    d.rgb[k][3 * i] = a[2]; d.rgb[k][3 * i + 1] = a[3]; d.rgb[k][3 * i + 2] = a[4];
+    *reinterpret_cast<float4 *>(d.co[k] + 4 * i) = make_float4(a[5], a[6], a[7], a[8]);
+}
+
+extern "C" int gs_xchg_scatter_grad(int B, int P, int W, const uint8_t *flags, const int32_t *gpos,
+                                    const float *grad_rows, void *const *d_means2D_ptrs_host,
+                                    void *const *d_rgb_ptrs_host, void *const *d_conic_opacity_ptrs_host, void *stream) {
+    GS_REQUIRE(B > 0 && B <= XB && W > 0 && W <= XW && P >= 0, "sizes");
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(flags && gpos && grad_rows && d_means2D_ptrs_host && d_rgb_ptrs_host && d_conic_opacity_ptrs_host,
+               "null pointer");
+    XOut d;
+    for (int k = 0; k < XB; k++) {
+        d.m2[k] = k < B ? (float *)d_means2D_ptrs_host[k] : nullptr;
+        d.rgb[k] = k < B ? (float *)d_rgb_ptrs_host[k] : nullptr;
+        d.co[k] = k < B ? (float *)d_conic_opacity_ptrs_host[k] : nullptr;
+        d.rad[k] = nullptr; d.dep[k] = nullptr;
+    }
+    GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
+    dim3 grid((P + DT_THREADS - 1) / DT_THREADS, B);
+    k_xchg_scatter_grad<<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(B, P, W, flags, gpos, grad_rows, d);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

@@ -46,6 +46,12 @@ SIGNATURES = {
     "gs_unpack_rows": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_pack_grad_rows": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_scatter_grad_rows": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_xchg_temp_bytes": (_sz, [_i, _i, _i]),
+    "gs_xchg_route": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gs_xchg_pack": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_xchg_unpack": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_xchg_pack_grad": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gs_xchg_scatter_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -87,28 +87,27 @@ def gather_counts(local_counts, group=None):
 
 
 # ---------------------------------------------------------------------------------------------------
-# device side
+# device side (batched: one launch per stage for all B cameras of the step)
 # ---------------------------------------------------------------------------------------------------
 def _i32(vals):
     return (C.c_int32 * len(vals))(*[int(v) for v in vals])
 
 
-class Route:
-    """Per-camera routing state: mask (P, ncols), scan positions, column starts."""
+def _ptrs(tensors):
+    return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
 
-    def __init__(self, mask, gpu_ids):
-        P, ncols = mask.shape
-        self.mask, self.gpu_ids, self.P, self.ncols = mask.contiguous(), list(gpu_ids), P, ncols
-        dev = mask.device
-        self.gpos = torch.empty((max(P * ncols, 1),), dtype=torch.int32, device=dev)
-        self.colstart = torch.empty((ncols + 1,), dtype=torch.int32, device=dev)
-        tb = _lib.query("gs_route_scan_temp_bytes", P, ncols)
-        temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
-        _lib.call("gs_route_scan", P, ncols, self.mask.data_ptr(), self.gpos.data_ptr(), self.colstart.data_ptr(),
-                  temp.data_ptr(), tb, ops._stream())
 
-    def counts(self):
-        return self.colstart[1:] - self.colstart[:-1]
+def segments(layout):
+    """(recv_start, length, camera, dst_start) of every (source rank, camera) block of the recv buffer, in recv
+    order; dst_start is the block's first row inside that camera's concatenated output."""
+    rs, ln, cam, ds = [], [], [], []
+    for i in range(layout.W):
+        for k in range(layout.B):
+            rs.append(layout.seg_off[k][i])
+            ln.append(layout.seg_len[k][i])
+            cam.append(k)
+            ds.append(sum(layout.seg_len[k][:i]))
+    return rs, ln, cam, ds
 
 
 class _ExchangeSplats(torch.autograd.Function):
@@ -117,63 +116,59 @@ class _ExchangeSplats(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, state, *tensors):
-        routes, layout, aux, group = state["routes"], state["layout"], state["aux"], state["group"]
-        B = len(routes)
+        layout, aux, group = state["layout"], state["aux"], state["group"]
+        B, P, W = state["B"], state["P"], state["W"]
         dev = tensors[0].device
         s = ops._stream()
+        m2s = [tensors[3 * k].contiguous() for k in range(B)]
+        rgbs = [tensors[3 * k + 1].contiguous() for k in range(B)]
+        cos = [tensors[3 * k + 2].contiguous() for k in range(B)]
         send = torch.empty((max(layout.total_send, 1), ROW), dtype=torch.float32, device=dev)
-        for k, r in enumerate(routes):
-            m2, rgb, co = (t.contiguous() for t in tensors[3 * k:3 * k + 3])
-            radii, depths = aux[k]
-            _lib.call("gs_pack_rows", r.P, r.ncols, r.mask.data_ptr(), r.gpos.data_ptr(), r.colstart.data_ptr(),
-                      _i32(layout.dst_off[k]), m2.data_ptr(), rgb.data_ptr(), co.data_ptr(), radii.data_ptr(),
-                      depths.data_ptr(), send.data_ptr(), s)
+        _lib.call("gs_xchg_pack", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), _ptrs(m2s), _ptrs(rgbs),
+                  _ptrs(cos), _ptrs([a[0] for a in aux]), _ptrs([a[1] for a in aux]), send.data_ptr(), s)
         recv = torch.empty((max(layout.total_recv, 1), ROW), dtype=torch.float32, device=dev)
         all_to_all_single(recv[:layout.total_recv], send[:layout.total_send], layout.recv_splits, layout.send_splits, group)
-        outs, auxs = [], []
-        for k in range(B):
-            n = layout.n_recv[k]
-            m2 = torch.empty((n, 2), dtype=torch.float32, device=dev)
-            rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
-            co = torch.empty((n, 4), dtype=torch.float32, device=dev)
-            radii = torch.empty((n,), dtype=torch.int32, device=dev)
-            depths = torch.empty((n,), dtype=torch.float32, device=dev)
-            if n:
-                _lib.call("gs_unpack_rows", layout.W, _i32(layout.seg_off[k]), _i32(layout.seg_len[k]), recv.data_ptr(),
-                          m2.data_ptr(), rgb.data_ptr(), co.data_ptr(), radii.data_ptr(), depths.data_ptr(), s)
-            outs += [m2, rgb, co]
-            auxs += [radii, depths]
+        om2 = [torch.empty((n, 2), dtype=torch.float32, device=dev) for n in layout.n_recv]
+        orgb = [torch.empty((n, 3), dtype=torch.float32, device=dev) for n in layout.n_recv]
+        oco = [torch.empty((n, 4), dtype=torch.float32, device=dev) for n in layout.n_recv]
+        orad = [torch.empty((n,), dtype=torch.int32, device=dev) for n in layout.n_recv]
+        odep = [torch.empty((n,), dtype=torch.float32, device=dev) for n in layout.n_recv]
+        rs, ln, cam, ds = state["segs"]
+        _lib.call("gs_xchg_unpack", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, recv.data_ptr(),
+                  B, _ptrs(om2), _ptrs(orgb), _ptrs(oco), _ptrs(orad), _ptrs(odep), s)
         ctx.state = state
+        outs = []
+        for k in range(B):
+            outs += [om2[k], orgb[k], oco[k]]
+        auxs = []
+        for k in range(B):
+            auxs += [orad[k], odep[k]]
         ctx.mark_non_differentiable(*auxs)
         return tuple(outs + auxs)
 
     @staticmethod
     def backward(ctx, *grads):
         state = ctx.state
-        routes, layout, group = state["routes"], state["layout"], state["group"]
-        B = len(routes)
-        dev = routes[0].mask.device
+        layout, group = state["layout"], state["group"]
+        B, P, W = state["B"], state["P"], state["W"]
+        dev = state["flags"].device
         s = ops._stream()
-        grecv = torch.zeros((max(layout.total_recv, 1), GROW), dtype=torch.float32, device=dev)
-        for k in range(B):
-            n = layout.n_recv[k]
-            if not n:
-                continue
-            g = []
-            for t, w in zip(grads[3 * k:3 * k + 3], (2, 3, 4)):
-                g.append(torch.zeros((n, w), dtype=torch.float32, device=dev) if t is None else t.contiguous())
-            _lib.call("gs_pack_grad_rows", layout.W, _i32(layout.seg_off[k]), _i32(layout.seg_len[k]), g[0].data_ptr(),
-                      g[1].data_ptr(), g[2].data_ptr(), grecv.data_ptr(), s)
+        g = [None if t is None else t.contiguous() for t in grads[:3 * B]]
+        grecv = torch.empty((max(layout.total_recv, 1), GROW), dtype=torch.float32, device=dev)
+        rs, ln, cam, ds = state["segs"]
+        _lib.call("gs_xchg_pack_grad", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, B,
+                  _ptrs([g[3 * k] for k in range(B)]), _ptrs([g[3 * k + 1] for k in range(B)]),
+                  _ptrs([g[3 * k + 2] for k in range(B)]), grecv.data_ptr(), s)
         gsend = torch.empty((max(layout.total_send, 1), GROW), dtype=torch.float32, device=dev)
         all_to_all_single(gsend[:layout.total_send], grecv[:layout.total_recv], layout.send_splits, layout.recv_splits, group)
+        d_m2 = [torch.empty((P, 2), dtype=torch.float32, device=dev) for _ in range(B)]
+        d_rgb = [torch.empty((P, 3), dtype=torch.float32, device=dev) for _ in range(B)]
+        d_co = [torch.empty((P, 4), dtype=torch.float32, device=dev) for _ in range(B)]
+        _lib.call("gs_xchg_scatter_grad", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), gsend.data_ptr(),
+                  _ptrs(d_m2), _ptrs(d_rgb), _ptrs(d_co), s)
         out = [None]
-        for k, r in enumerate(routes):
-            d_m2 = torch.empty((r.P, 2), dtype=torch.float32, device=dev)
-            d_rgb = torch.empty((r.P, 3), dtype=torch.float32, device=dev)
-            d_co = torch.empty((r.P, 4), dtype=torch.float32, device=dev)
-            _lib.call("gs_scatter_grad_rows", r.P, r.ncols, r.mask.data_ptr(), r.gpos.data_ptr(), r.colstart.data_ptr(),
-                      _i32(layout.dst_off[k]), gsend.data_ptr(), d_m2.data_ptr(), d_rgb.data_ptr(), d_co.data_ptr(), s)
-            out += [d_m2, d_rgb, d_co]
+        for k in range(B):
+            out += [d_m2[k], d_rgb[k], d_co[k]]
         return tuple(out)
 
 
@@ -183,21 +178,25 @@ def exchange(screen_params, strategies, settings, world, me, group=None):
     and the all-gathered counts cnt[i][k][j] (the reference's gpui_to_gpuj_imgk_size)."""
     B = len(screen_params)
     dev = screen_params[0][0].device
-    routes = []
-    local_counts = torch.zeros((B, world), dtype=torch.int32, device=dev)
-    for k, (m2, rgb, co, radii, depths) in enumerate(screen_params):
-        st = strategies[k]
-        rs = settings[k]
-        tile_x = (int(rs.image_width) + ops.BLOCK_X - 1) // ops.BLOCK_X
-        mask = ops.get_local2j_ids_bool(rs.image_height, rs.image_width, st.rank, st.world_size, m2, radii,
-                                        st.strategy_tensor(tile_x, dev))
-        r = Route(mask.view(torch.uint8), st.gpu_ids)
-        routes.append(r)
-        local_counts[k, torch.tensor(st.gpu_ids, device=dev)] = r.counts()
-    cnt = gather_counts(local_counts, group)
-    layout = Layout(cnt, me, [r.gpu_ids for r in routes])
-    state = dict(routes=routes, layout=layout, group=group,
-                 aux=[(p[3].to(torch.int32).contiguous(), p[4].contiguous()) for p in screen_params])
+    P = screen_params[0][0].shape[0]
+    H, Wimg = int(settings[0].image_height), int(settings[0].image_width)
+    lo, hi = [0] * (B * world), [0] * (B * world)
+    for k, st in enumerate(strategies):
+        for c, j in enumerate(st.gpu_ids):
+            lo[k * world + j], hi[k * world + j] = st.division_pos[c], st.division_pos[c + 1]
+    aux = [(p[3].to(torch.int32).contiguous(), p[4].contiguous()) for p in screen_params]
+    m2s = [p[0].detach().contiguous() for p in screen_params]
+    n = max(B * P * world, 1)
+    flags = torch.empty((n,), dtype=torch.uint8, device=dev)
+    gpos = torch.empty((n,), dtype=torch.int32, device=dev)
+    counts = torch.empty((world, B), dtype=torch.int32, device=dev)   # [dest j][camera k]
+    tb = _lib.query("gs_xchg_temp_bytes", B, P, world)
+    temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
+    _lib.call("gs_xchg_route", B, P, world, H, Wimg, _ptrs(m2s), _ptrs([a[0] for a in aux]), _i32(lo), _i32(hi),
+              flags.data_ptr(), gpos.data_ptr(), counts.data_ptr(), temp.data_ptr(), tb, ops._stream())
+    cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]
+    layout = Layout(cnt, me, [st.gpu_ids for st in strategies])
+    state = dict(layout=layout, group=group, aux=aux, flags=flags, gpos=gpos, B=B, P=P, W=world, segs=segments(layout))
     flat = []
     for p in screen_params:
         flat += [p[0], p[1], p[2]]

@@ -212,6 +212,32 @@ GS_API int gs_scatter_grad_rows(int P, int ncols, const uint8_t *mask, const int
                                 const int32_t *src_off_host, const float *rows, float *d_means2D, float *d_rgb,
                                 float *d_conic_opacity, void *stream);
 
+/* Batched form: ALL B cameras of a step per launch (B, W <= 16; B*W <= 128 non-empty (source, camera) segments).
+ * Flags / scan positions are laid out [destination rank j][camera k][splat i] -- the all_to_all_single send layout --
+ * so gpos IS the row index in the send buffer.  *_ptrs_host are HOST arrays of B device pointers (one per camera);
+ * row_lo/row_hi_host are HOST (B*W) tile-row ranges [lo,hi) of camera k owned by global rank j (row strips of
+ * workload_division.py:852-941).  counts: (W*B) int32 device, [j][k]. */
+GS_API size_t gs_xchg_temp_bytes(int B, int P, int W);
+GS_API int gs_xchg_route(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                         const void *const *radii_ptrs_host, const int32_t *row_lo_host, const int32_t *row_hi_host,
+                         uint8_t *flags, int32_t *gpos, int32_t *counts, void *temp, size_t temp_bytes, void *stream);
+GS_API int gs_xchg_pack(int B, int P, int W, const uint8_t *flags, const int32_t *gpos,
+                        const void *const *means2D_ptrs_host, const void *const *rgb_ptrs_host,
+                        const void *const *conic_opacity_ptrs_host, const void *const *radii_ptrs_host,
+                        const void *const *depths_ptrs_host, float *send_rows, void *stream);
+GS_API int gs_xchg_unpack(int nseg, const int32_t *seg_recv_start_host, const int32_t *seg_len_host,
+                          const int32_t *seg_cam_host, const int32_t *seg_dst_start_host, int total_rows,
+                          const float *recv_rows, int B, void *const *means2D_ptrs_host, void *const *rgb_ptrs_host,
+                          void *const *conic_opacity_ptrs_host, void *const *radii_ptrs_host,
+                          void *const *depths_ptrs_host, void *stream);
+GS_API int gs_xchg_pack_grad(int nseg, const int32_t *seg_recv_start_host, const int32_t *seg_len_host,
+                             const int32_t *seg_cam_host, const int32_t *seg_dst_start_host, int total_rows, int B,
+                             const void *const *d_means2D_ptrs_host, const void *const *d_rgb_ptrs_host,
+                             const void *const *d_conic_opacity_ptrs_host, float *grad_rows, void *stream);
+GS_API int gs_xchg_scatter_grad(int B, int P, int W, const uint8_t *flags, const int32_t *gpos, const float *grad_rows,
+                                void *const *d_means2D_ptrs_host, void *const *d_rgb_ptrs_host,
+                                void *const *d_conic_opacity_ptrs_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
