@@ -55,13 +55,16 @@ GS_D uint32_t block_mask(float mx, float my, float ex, float ey, float X0, float
     return m;
 }
 
+// staged splat: one 48-byte slot so a single address feeds all three shared-memory loads
+struct __align__(16) SRec { float4 a; float4 b; float4 c; };
+
+template <bool STATS>
 __global__ void __launch_bounds__(BL_THREADS)
 k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restrict__ bg,
             const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
             const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
             uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats) {
-    __shared__ float4 s_r0[FW_CHUNK], s_r1[FW_CHUNK];
-    __shared__ float2 s_gb[FW_CHUNK];
+    __shared__ SRec s_rec[FW_CHUNK];
     __shared__ uint8_t s_cull[FW_CHUNK];
     __shared__ unsigned long long s_stats[3];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
@@ -91,18 +94,19 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             const uint32_t g = ids[range.x + base + threadIdx.x];
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-            s_r0[threadIdx.x] = a; s_r1[threadIdx.x] = b; s_gb[threadIdx.x] = make_float2(c.x, c.y);
+            s_rec[threadIdx.x].a = a; s_rec[threadIdx.x].b = b; s_rec[threadIdx.x].c = c;
             s_cull[threadIdx.x] = (uint8_t)block_mask(a.x, a.y, c.z, c.w, X0, Y0);
         }
         __syncthreads();
-        bool wdone = __all_sync(0xffffffffu, done);
-        for (int g0 = 0; g0 < cnt && !wdone; g0 += 32) {
+        for (int g0 = 0; g0 < cnt; g0 += 32) {
+            if (__all_sync(0xffffffffu, done)) break;  // checked once per 32 entries; finished pixels are NaN anyway
             const int jj = g0 + lane;
             uint32_t cand = __ballot_sync(0xffffffffu, jj < cnt && ((s_cull[jj] >> warp) & 1));
             while (cand) {
                 const int j = g0 + __ffs(cand) - 1;
                 cand &= cand - 1;
-                const float4 a = s_r0[j], b = s_r1[j];
+                const SRec *sr = &s_rec[j];
+                const float4 a = sr->a, b = sr->b;
                 const float dx = a.x - pxf, dy = a.y - pyf;
                 const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
                 const bool ok = power >= b.z;  // false for NaN (finished / outside pixels)
@@ -114,18 +118,17 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
                         if (test_T < T_EPS) {
                             done = true;
                             pxf = qnan;
-                            considered = (uint32_t)(base + j + 1);
+                            if (STATS) considered = (uint32_t)(base + j + 1);
                         } else {
-                            const float2 gb = s_gb[j];
+                            const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
                             const float w = alpha * T;
                             C0 += b.w * w; C1 += gb.x * w; C2 += gb.y * w;
                             T = test_T;
                             last = (uint32_t)(base + j + 1);
-                            blended++;
+                            if (STATS) blended++;
                         }
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) { wdone = true; break; }
             }
         }
     }
@@ -137,7 +140,7 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
         n_contrib[pix] = last;
         if (considered == 0) considered = (uint32_t)total;
     }
-    if (stats) {  // stages 81-83: sums of tile-list length / entries walked / entries blended
+    if (STATS) {  // stages 81-83: sums of tile-list length / entries walked / entries blended
         if (threadIdx.x < 3) s_stats[threadIdx.x] = 0ull;
         __syncthreads();
         unsigned long long v0 = inside ? (unsigned long long)total : 0ull, v1 = inside ? considered : 0u,
@@ -190,8 +193,7 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
             const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
             float *__restrict__ d_means2D, float *__restrict__ d_conic_opacity, float *__restrict__ d_rgb) {
-    __shared__ float4 s_r0[BW_CHUNK], s_r1[BW_CHUNK];
-    __shared__ float2 s_gb[BW_CHUNK];
+    __shared__ SRec s_rec[BW_CHUNK];
     __shared__ uint32_t s_id[BW_CHUNK];
     __shared__ uint8_t s_cull[BW_CHUNK];
     __shared__ float s_acc[BL_WARPS][9][BW_STRIDE];
@@ -236,7 +238,7 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             s_id[threadIdx.x] = g;
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), cc = __ldg(r + 2);
-            s_r0[threadIdx.x] = a; s_r1[threadIdx.x] = b; s_gb[threadIdx.x] = make_float2(cc.x, cc.y);
+            s_rec[threadIdx.x].a = a; s_rec[threadIdx.x].b = b; s_rec[threadIdx.x].c = cc;
             s_cull[threadIdx.x] = (uint8_t)block_mask(a.x, a.y, cc.z, cc.w, X0, Y0);
         }
         uint32_t wmask = 0u;  // lane q holds bits [32q, 32q+32) of "this warp produced a partial for entry j"
@@ -250,7 +252,8 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
                     const int b31 = 31 - __clz(cand);
                     const int j = g0 + b31;
                     cand &= ~(1u << b31);
-                    const float4 a = s_r0[j], b = s_r1[j];
+                    const SRec *sr = &s_rec[j];
+                    const float4 a = sr->a, b = sr->b;
                     const float dx = a.x - pxf, dy = a.y - pyf;
                     const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
                     bool ok = ((uint32_t)(base + j) < last) && power >= b.z;
@@ -264,7 +267,7 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
                     // constants once per (splat, tile) in the flush below.
                     float v[9];
                     {
-                        const float2 gb = s_gb[j];
+                        const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
                         const float one_m = 1.f - alpha;
                         const float inv = __fdividef(1.f, one_m);
                         const float Tn = T * inv;
@@ -306,7 +309,7 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             }
             if (any) {
                 const uint32_t g = s_id[j];
-                const float4 a = s_r0[j], b = s_r1[j];  // (mx,my,a',b') (c',opacity,thr,red); A=-2a' B=-b' C=-2c'
+                const float4 a = s_rec[j].a, b = s_rec[j].b;  // (mx,my,a',b') (c',opacity,thr,red); A=-2a' B=-b' C=-2c'
                 // d power/d mean = (2a'dx + b'dy, 2c'dy + b'dx); dL/dmeans2D is per NDC unit: * (W/2, H/2)
                 atomicAdd(d_means2D + 2 * (size_t)g, (2.f * a.z * s[0] + a.w * s[1]) * ddelx_dx);
                 atomicAdd(d_means2D + 2 * (size_t)g + 1, (2.f * b.x * s[1] + a.w * s[0]) * ddely_dy);
@@ -329,9 +332,15 @@ int gs_launch_blend_forward(int64_t R, int H, int W, const float *rec, const flo
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     if (stats) GS_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t), stream));
     GsStageTimer timer(GS_STAGE_BLEND_FWD, stream);
-    k_blend_fwd<<<gx * gy, BL_THREADS, 0, stream>>>(W, H, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
-                                                    reinterpret_cast<const uint2 *>(ranges), ids_sorted, image, final_T,
-                                                    n_contrib, reinterpret_cast<unsigned long long *>(stats));
+    auto *st = reinterpret_cast<unsigned long long *>(stats);
+    if (stats)
+        k_blend_fwd<true><<<gx * gy, BL_THREADS, 0, stream>>>(W, H, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
+                                                              reinterpret_cast<const uint2 *>(ranges), ids_sorted, image,
+                                                              final_T, n_contrib, st);
+    else
+        k_blend_fwd<false><<<gx * gy, BL_THREADS, 0, stream>>>(W, H, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
+                                                               reinterpret_cast<const uint2 *>(ranges), ids_sorted, image,
+                                                               final_T, n_contrib, st);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
