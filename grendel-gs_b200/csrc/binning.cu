@@ -16,7 +16,7 @@
 //   r0 = (mx, my, a', b')      a' = -A/2, b' = -B, c' = -C/2  so that  power = a'dx^2 + b'dx dy + c'dy^2
 //   r1 = (c', opacity, thr, red)     thr = ln(1/(255*opacity)) - margin: power < thr  =>  alpha < 1/255
 //   r2 = (green, blue, ex, ey)       half extents of the bounding box of {power >= thr} (+0.5 px slack),
-//                                    used by the blend kernels to cull splats per 8x4 pixel block
+//                                    used by the blend kernels to cull splats per 4x4 pixel block
 #define GS_THR_MARGIN 0.02f
 __global__ void __launch_bounds__(BIN_THREADS)
 k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const float *__restrict__ conic_opacity,

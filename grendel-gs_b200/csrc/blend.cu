@@ -4,31 +4,37 @@
 // (/root/reference/gaussian_renderer/__init__.py:1271-1282, train_internal.py:195).
 //
 // One CTA = one 16x16 tile (BLOCK_X/Y are observable through _C.get_block_XY and baked into the
-// reference's strip arithmetic, loss_distribution.py:2321-2330); each warp owns an 8x4 pixel block.
-// Both kernels are bound by instruction issue over (pixel, splat) pairs, not by HBM (ncu: issue slots
-// ~88 % busy, DRAM ~2 %; algorithmic traffic is only 40 B / 76 B per instance), so the
-// design minimises instructions per pair:
-//   * sorted splat ids are turned into 48-byte packed records (3 x float4, built by k_count_tiles) staged in
-//     shared memory together with an 8-bit "which 8x4 blocks can this splat reach" mask computed from the
-//     bounding box of its {alpha >= 1/255} ellipse; a warp ballots 32 masks at a time and only walks the
-//     splats that can touch its block (conservative: per-pixel results are unchanged);
+// reference's strip arithmetic, loss_distribution.py:2321-2330).  Both kernels are bound by instruction
+// issue over (pixel, splat) pairs, not by HBM (ncu: issue slots ~85 % busy, DRAM ~2 %; algorithmic
+// traffic is only 40 B / 76 B per instance), so the design minimises issued instructions
+// per USEFUL pair:
+//   * the tile is cut into sixteen 4x4 pixel blocks; every HALF-warp owns one block and walks its own
+//     candidate list, so one warp instruction advances two (block, splat) pairs and ~60 % of the lanes do
+//     useful work in the blend path (an 8x4 block per full warp reached 37 %);
+//   * candidates come from a 16-bit "which 4x4 blocks can this splat reach" mask computed at staging time
+//     from the bounding box of the splat's {alpha >= 1/255} ellipse (conservative: per-pixel results are
+//     unchanged); a warp ballots 32 masks at a time;
 //   * the alpha < 1/255 test is done on the exponent (power < ln(1/(255 o)) - margin) so rejected pairs never
-//     reach MUFU.EX2; terminated pixels carry NaN coordinates so they drop out with no extra test;
-//   * backward reduction hierarchy (replaces the 9 global atomics per pixel per splat of the classical
-//     design): lane -> warp by a 9-value transposing butterfly (14 shuffles instead of 45) -> per-warp private
-//     shared-memory slots (no shared atomics: sm_100 has no native fp32 ATOMS.ADD) -> one thread per splat
-//     sums the warps and issues ONE set of global RED.ADD per (splat, tile).
+//     reach MUFU.EX2; finished / out-of-image pixels carry NaN coordinates so they fail it for free;
+//   * sorted splat ids are turned into 48-byte packed records (3 x float4, built by k_count_tiles), gathered
+//     once per (splat, tile) into shared memory;
+//   * backward: per-pixel weight m = dL/dG * G; its six moments (sum m, m dx, m dy, m dx^2, m dx dy, m dy^2) and
+//     three colour sums are reduced over the 16 lanes of the block by a 9-value transposing butterfly
+//     (12 shuffles instead of 36), stored in per-block private shared-memory slots (no shared atomics: sm_100
+//     has no native fp32 ATOMS.ADD -- it compiles to a CAS loop), then ONE thread per splat sums the blocks,
+//     applies the splat's constants and issues ONE set of 9 global RED.ADD per (splat, tile) -- instead of
+//     9 atomics per (splat, pixel) in the classical design.
 #include "common.cuh"
 
 #define BL_THREADS 256
 #define BL_WARPS (BL_THREADS / 32)
+#define BL_BLOCKS 16  // 4x4 pixel blocks per tile
 #define FW_CHUNK 256
-#define BW_CHUNK 128
-#define BW_STRIDE (BW_CHUNK + 1)
 
 #define ALPHA_MIN (1.0f / 255.0f)
 #define ALPHA_MAX 0.99f
 #define T_EPS 0.0001f
+#define FULL 0xffffffffu
 
 // exp(x) for x <= 0 as one FMUL + MUFU.EX2 (results below 2^-126 flush to 0: far under the 1/255 alpha floor)
 GS_D float gs_exp_neg(float x) {
@@ -37,21 +43,31 @@ GS_D float gs_exp_neg(float x) {
     return y;
 }
 
-GS_D void pixel_of_thread(int tile, int gx, int &px, int &py) {
+// thread -> (4x4 block, pixel).  Warp w holds blocks 2w and 2w+1 (horizontal neighbours), one per half-warp.
+struct Where { int blk, px, py, half, l16; };
+GS_D Where where_am_i(int tile, int gx) {
+    Where p;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    px = (tile % gx) * GS_BLOCK_X + (w & 1) * 8 + (lane & 7);
-    py = (tile / gx) * GS_BLOCK_Y + (w >> 1) * 4 + (lane >> 3);
+    p.half = lane >> 4;
+    p.l16 = lane & 15;
+    const int by = w >> 1, bx = (w & 1) * 2 + p.half;
+    p.blk = by * 4 + bx;
+    p.px = (tile % gx) * GS_BLOCK_X + bx * 4 + (p.l16 & 3);
+    p.py = (tile / gx) * GS_BLOCK_Y + by * 4 + (p.l16 >> 2);
+    return p;
 }
 
-// bit w set <=> the splat's bounding box (centre m, half extents e) overlaps warp w's 8x4 pixel block
-GS_D uint32_t block_mask(float mx, float my, float ex, float ey, float X0, float Y0) {
+// bit (by*4+bx) set <=> the splat's bounding box (centre m, half extents e) overlaps 4x4 block (bx,by)
+GS_D uint32_t block_mask16(float mx, float my, float ex, float ey, float X0, float Y0) {
     if (ex < 0.f) return 0u;
     const float xl = mx - ex - X0, xh = mx + ex - X0, yl = my - ey - Y0, yh = my + ey - Y0;
-    const uint32_t xm = ((xh >= 0.f && xl <= 7.f) ? 1u : 0u) | ((xh >= 8.f && xl <= 15.f) ? 2u : 0u);
-    uint32_t m = 0u;
+    uint32_t xm = 0u, m = 0u;
 #pragma unroll
-    for (int wy = 0; wy < 4; wy++)
-        if (yh >= 4.f * wy && yl <= 4.f * wy + 3.f) m |= xm << (2 * wy);
+    for (int b = 0; b < 4; b++)
+        if (xh >= 4.f * b && xl <= 4.f * b + 3.f) xm |= 1u << b;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (yh >= 4.f * b && yl <= 4.f * b + 3.f) m |= xm << (4 * b);
     return m;
 }
 
@@ -65,13 +81,13 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
             uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats) {
     __shared__ SRec s_rec[FW_CHUNK];
-    __shared__ uint8_t s_cull[FW_CHUNK];
+    __shared__ uint16_t s_cull[FW_CHUNK];
     __shared__ unsigned long long s_stats[3];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
     const int tile = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int px, py;
-    pixel_of_thread(tile, gx, px, py);
+    const int lane = threadIdx.x & 31;
+    const Where me = where_am_i(tile, gx);
+    const int px = me.px, py = me.py;
     const bool inside = px < W && py < H;
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
@@ -87,6 +103,7 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
     float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0, blended = 0, considered = 0;
     bool done = !inside;
+    const int blkA = me.blk - me.half;  // block of lanes 0-15; lanes 16-31 own blkA + 1
     for (int base = 0; base < total; base += FW_CHUNK) {
         if (__syncthreads_count(done) == BL_THREADS) break;
         const int cnt = min(FW_CHUNK, total - base);
@@ -95,22 +112,25 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
             s_rec[threadIdx.x].a = a; s_rec[threadIdx.x].b = b; s_rec[threadIdx.x].c = c;
-            s_cull[threadIdx.x] = (uint8_t)block_mask(a.x, a.y, c.z, c.w, X0, Y0);
+            s_cull[threadIdx.x] = (uint16_t)block_mask16(a.x, a.y, c.z, c.w, X0, Y0);
         }
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {
-            if (__all_sync(0xffffffffu, done)) break;  // checked once per 32 entries; finished pixels are NaN anyway
+            if (__all_sync(FULL, done)) break;  // checked once per 32 entries; finished pixels are NaN anyway
             const int jj = g0 + lane;
-            uint32_t cand = __ballot_sync(0xffffffffu, jj < cnt && ((s_cull[jj] >> warp) & 1));
-            while (cand) {
-                const int j = g0 + __ffs(cand) - 1;
-                cand &= cand - 1;
+            const uint32_t m = jj < cnt ? (uint32_t)s_cull[jj] : 0u;
+            const uint32_t cA = __ballot_sync(FULL, (m >> blkA) & 1u), cB = __ballot_sync(FULL, (m >> (blkA + 1)) & 1u);
+            uint32_t mine = me.half ? cB : cA;  // this half-warp's candidates among the 32 entries
+            while (__any_sync(FULL, mine != 0u)) {
+                const bool has = mine != 0u;
+                const int j = g0 + (has ? __ffs(mine) - 1 : 0);
+                mine &= mine - 1u;
                 const SRec *sr = &s_rec[j];
                 const float4 a = sr->a, b = sr->b;
                 const float dx = a.x - pxf, dy = a.y - pyf;
                 const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
-                const bool ok = power >= b.z;  // false for NaN (finished / outside pixels)
-                if (!__any_sync(0xffffffffu, ok)) continue;
+                const bool ok = has && power >= b.z;  // false for NaN (finished / outside pixels)
+                if (!__any_sync(FULL, ok)) continue;
                 if (ok && power <= 0.f) {
                     const float alpha = fminf(ALPHA_MAX, b.y * gs_exp_neg(power));
                     if (alpha >= ALPHA_MIN) {
@@ -147,14 +167,40 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
                            v2 = inside ? blended : 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            v0 += __shfl_xor_sync(FULL, v0, o);
+            v1 += __shfl_xor_sync(FULL, v1, o);
+            v2 += __shfl_xor_sync(FULL, v2, o);
         }
         if (lane == 0) { atomicAdd(&s_stats[0], v0); atomicAdd(&s_stats[1], v1); atomicAdd(&s_stats[2], v2); }
         __syncthreads();
         if (threadIdx.x < 3) atomicAdd(&stats[threadIdx.x], s_stats[threadIdx.x]);
     }
+}
+
+// ---- backward -------------------------------------------------------------------------------------------
+// The backward keeps one 8x4 pixel block per FULL warp (8-bit cull mask, 128-entry chunks): the half-warp /
+// 4x4 layout that helps the forward was measured slower here (2.18 vs 1.77 ms on c2) -- sixteen private
+// partial-sum slots force 64-entry chunks, and the extra barriers + 64-thread flush cost more (barrier stalls
+// 3.1 warps per issue) than the better lane utilisation returns.
+#define BW8_CHUNK 128
+#define BW8_STRIDE (BW8_CHUNK + 1)
+
+GS_D void pixel_of_thread(int tile, int gx, int &px, int &py) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    px = (tile % gx) * GS_BLOCK_X + (w & 1) * 8 + (lane & 7);
+    py = (tile / gx) * GS_BLOCK_Y + (w >> 1) * 4 + (lane >> 3);
+}
+
+// bit w set <=> the splat's bounding box (centre m, half extents e) overlaps warp w's 8x4 pixel block
+GS_D uint32_t block_mask(float mx, float my, float ex, float ey, float X0, float Y0) {
+    if (ex < 0.f) return 0u;
+    const float xl = mx - ex - X0, xh = mx + ex - X0, yl = my - ey - Y0, yh = my + ey - Y0;
+    const uint32_t xm = ((xh >= 0.f && xl <= 7.f) ? 1u : 0u) | ((xh >= 8.f && xl <= 15.f) ? 2u : 0u);
+    uint32_t m = 0u;
+#pragma unroll
+    for (int wy = 0; wy < 4; wy++)
+        if (yh >= 4.f * wy && yl <= 4.f * wy + 3.f) m |= xm << (2 * wy);
+    return m;
 }
 
 // 9-value warp reduction.  After the call every lane holds in v[0] the warp total of value
@@ -193,11 +239,11 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
             const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
             const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
             float *__restrict__ d_means2D, float *__restrict__ d_conic_opacity, float *__restrict__ d_rgb) {
-    __shared__ SRec s_rec[BW_CHUNK];
-    __shared__ uint32_t s_id[BW_CHUNK];
-    __shared__ uint8_t s_cull[BW_CHUNK];
-    __shared__ float s_acc[BL_WARPS][9][BW_STRIDE];
-    __shared__ uint32_t s_mask[BL_WARPS][BW_CHUNK / 32];
+    __shared__ SRec s_rec[BW8_CHUNK];
+    __shared__ uint32_t s_id[BW8_CHUNK];
+    __shared__ uint8_t s_cull[BW8_CHUNK];
+    __shared__ float s_acc[BL_WARPS][9][BW8_STRIDE];
+    __shared__ uint32_t s_mask[BL_WARPS][BW8_CHUNK / 32];
     __shared__ uint32_t s_max[BL_WARPS];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
     const int tile = blockIdx.x;
@@ -228,10 +274,10 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
     for (int w = 0; w < BL_WARPS; w++) n_total = max(n_total, s_max[w]);
     const uint32_t wlast = m;  // deepest entry this warp's pixels reach
     float T = T_final, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
-    const int n_chunks = ((int)n_total + BW_CHUNK - 1) / BW_CHUNK;
+    const int n_chunks = ((int)n_total + BW8_CHUNK - 1) / BW8_CHUNK;
     for (int c = n_chunks - 1; c >= 0; c--) {
-        const int base = c * BW_CHUNK;
-        const int cnt = min(BW_CHUNK, (int)n_total - base);
+        const int base = c * BW8_CHUNK;
+        const int cnt = min(BW8_CHUNK, (int)n_total - base);
         __syncthreads();  // previous chunk's flush has finished reading shared memory
         if ((int)threadIdx.x < cnt) {
             const uint32_t g = ids[range.x + base + threadIdx.x];
@@ -291,7 +337,7 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
                 if (lane == (g0 >> 5)) wmask = mybits;
             }
         }
-        if (lane < BW_CHUNK / 32) s_mask[warp][lane] = wmask;
+        if (lane < BW8_CHUNK / 32) s_mask[warp][lane] = wmask;
         __syncthreads();
         if ((int)threadIdx.x < cnt) {
             const int j = threadIdx.x;
