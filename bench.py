@@ -249,8 +249,20 @@ def run_ours(args):
     else:
         dom_bytes = ab["binning"] / units
     achieved = dom_bytes / (per_stage[dom] * 1e-3) / 1e9
+    # DRAM bytes per launch and issue-slot utilisation of that kernel from the committed ncu --set full capture
+    # (profiles/traffic.json; only valid for the workload it was captured on: c2 at N=1)
+    traffic, secondary = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["stages"]
+        if dom in tj and args.workload == "c2" and world == 1 and not args.n:
+            traffic = tj[dom]["dram_bytes_per_launch"]
+            secondary = {"bound": "instruction issue", "issue_slots_busy_pct": tj[dom]["issue_active_pct"],
+                         "note": "blend kernels do 256 (pixel,splat) evaluations per 40-76 B instance: issue-bound, "
+                                 "HBM idle by construction (SURVEY.md 8d)", "source": "profiles/r1_all_kernels_ncu.md"}
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "secondary_bound": secondary, "peak_source": peak_src,
                 "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": per_stage[dom],
                 "stage_ms_per_launch": {k: round(v, 4) for k, v in per_stage.items()},
                 "step_alg_bytes": float(sum(ab.values())),
@@ -267,7 +279,10 @@ def run_ours(args):
                        "loss_check": loss_host},
             "e2e": {"value": N * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(sum(launches.values())), "roofline": roofline, "clocks": clocks}
+            "gpu_launches": int(sum(v for k, v in launches.items() if k not in ("30 InclusiveSum", "50 SortPairs"))),
+            "library_calls": {"cub::DeviceScan": int(launches.get("30 InclusiveSum", 0)),
+                              "cub::DeviceRadixSort": int(launches.get("50 SortPairs", 0))},
+            "roofline": roofline, "clocks": clocks}
     if not args.no_cpu_baseline:
         r = cpu_arm(cfg, args.cpu_sample, 1, 1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
