@@ -273,7 +273,10 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
 #pragma unroll
     for (int w = 0; w < BL_WARPS; w++) n_total = max(n_total, s_max[w]);
     const uint32_t wlast = m;  // deepest entry this warp's pixels reach
-    float T = T_final, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
+    // B = colour of everything behind the current splat (back-to-front recurrence B += alpha (c - B)); with alpha
+    // forced to 0 for lanes that do not blend this splat every state update below is a no-op for them, so the
+    // blend path needs no per-lane branches or conditional moves.
+    float T = T_final, B0 = 0.f, B1 = 0.f, B2 = 0.f;
     const int n_chunks = ((int)n_total + BW8_CHUNK - 1) / BW8_CHUNK;
     for (int c = n_chunks - 1; c >= 0; c--) {
         const int base = c * BW8_CHUNK;
@@ -314,17 +317,15 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
                     float v[9];
                     {
                         const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
-                        const float one_m = 1.f - alpha;
-                        const float inv = __fdividef(1.f, one_m);
-                        const float Tn = T * inv;
-                        const float n0 = acc0 + last_alpha * (lc0 - acc0);
-                        const float n1 = acc1 + last_alpha * (lc1 - acc1);
-                        const float n2 = acc2 + last_alpha * (lc2 - acc2);
-                        float dL_dalpha = (b.w - n0) * dp0 + (gb.x - n1) * dp1 + (gb.y - n2) * dp2;
-                        dL_dalpha = dL_dalpha * Tn - (T_final * inv) * bgdot;
+                        const float ae = ok ? alpha : 0.f;   // effective alpha: 0 = this lane skips the splat
+                        float inv;                            // 1/(1-ae), 1-ae in [0.01, 1]: one MUFU.RCP
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - ae));
+                        T = T * inv;                          // transmittance in front of this splat
+                        const float d0 = b.w - B0, d1 = gb.x - B1, d2 = gb.y - B2;
+                        const float dL_dalpha = (d0 * dp0 + d1 * dp1 + d2 * dp2) * T - (T_final * inv) * bgdot;
                         const float mw = ok ? b.y * dL_dalpha * G : 0.f;
-                        const float dch = ok ? alpha * Tn : 0.f;
-                        if (ok) { T = Tn; acc0 = n0; acc1 = n1; acc2 = n2; lc0 = b.w; lc1 = gb.x; lc2 = gb.y; last_alpha = alpha; }
+                        const float dch = ae * T;
+                        B0 += ae * d0; B1 += ae * d1; B2 += ae * d2;
                         const float mx_ = mw * dx, my_ = mw * dy;
                         v[0] = mx_; v[1] = my_; v[2] = mx_ * dx; v[3] = mx_ * dy; v[4] = my_ * dy; v[5] = mw;
                         v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;

@@ -583,3 +583,77 @@ extern "C" int gs_xchg_scatter_grad(int B, int P, int W, const uint8_t *flags, c
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
+
+// ---- sparse per-Gaussian gradient all-reduce staging (replicated-Gaussian data parallelism) ------------------
+// /root/reference/scene/gaussian_model.py:1332-1391 (get_sparse_ids / sync_gradients_sparsely): rows whose
+// _xyz.grad is non-zero on ANY rank are compacted, all-reduced and scattered back -- per parameter, i.e. 1 + 6
+// collectives and 12 gather/scatter kernels.  Here the six gradients of a touched Gaussian travel as ONE 59-float
+// row (xyz 3, features_dc 3, features_rest 45, scaling 3, rotation 4, opacity 1), so the step is: mask kernel ->
+// all-reduce(MAX) of the byte mask -> scan -> pack -> ONE all-reduce(SUM) -> unpack.  (The reference lists this
+// "fused_sparse" mode as NotImplemented, gaussian_model.py:1438-1439.)
+#define SG_FLOATS 59
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_sparse_mask(int P, const float *__restrict__ xyz_grad, uint8_t *__restrict__ mask) {
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x;
+    if (i >= P) return;
+    mask[i] = (xyz_grad[3 * i] != 0.f || xyz_grad[3 * i + 1] != 0.f || xyz_grad[3 * i + 2] != 0.f) ? 1 : 0;
+}
+
+extern "C" int gs_sparse_grad_mask(int P, const float *xyz_grad, uint8_t *mask, void *stream) {
+    GS_REQUIRE(P >= 0, "P");
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(xyz_grad && mask, "null pointer");
+    k_sparse_mask<<<(P + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(P, xyz_grad, mask);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+struct SgPtrs { float *p[6]; };
+
+template <bool PACK>
+__global__ void __launch_bounds__(DT_THREADS)
+k_sparse_rows(int P, const uint8_t *__restrict__ mask, const int32_t *__restrict__ pos, SgPtrs g,
+              float *__restrict__ rows) {
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x;
+    if (i >= P || !mask[i]) return;
+    float *r = rows + (size_t)pos[i] * SG_FLOATS;
+    const int width[6] = {3, 3, 45, 3, 4, 1};
+    int o = 0;
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+        float *src = g.p[t] + (size_t)i * width[t];
+        for (int q = 0; q < width[t]; q++) {
+            if (PACK) r[o + q] = src[q]; else src[q] = r[o + q];
+        }
+        o += width[t];
+    }
+}
+
+// grads_host: HOST array of the six device gradient pointers in GaussianModel order
+// (_xyz, _features_dc, _features_rest, _scaling, _rotation, _opacity); pos: exclusive scan of mask (gs_route_scan
+// with ncols = 1); rows: (n_touched, 59).
+extern "C" int gs_sparse_grad_pack(int P, const uint8_t *mask, const int32_t *pos, void *const *grads_host,
+                                   float *rows, void *stream) {
+    GS_REQUIRE(P >= 0, "P");
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(mask && pos && grads_host && rows, "null pointer");
+    SgPtrs g;
+    for (int t = 0; t < 6; t++) { g.p[t] = (float *)grads_host[t]; GS_REQUIRE(g.p[t] != nullptr, "null gradient"); }
+    k_sparse_rows<true><<<(P + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(P, mask, pos, g, rows);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_sparse_grad_unpack(int P, const uint8_t *mask, const int32_t *pos, const float *rows,
+                                     void *const *grads_host, void *stream) {
+    GS_REQUIRE(P >= 0, "P");
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(mask && pos && grads_host && rows, "null pointer");
+    SgPtrs g;
+    for (int t = 0; t < 6; t++) { g.p[t] = (float *)grads_host[t]; GS_REQUIRE(g.p[t] != nullptr, "null gradient"); }
+    k_sparse_rows<false><<<(P + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(
+        P, mask, pos, g, const_cast<float *>(rows));
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

@@ -58,14 +58,6 @@ class GaussianRasterizer(nn.Module):
         return image, radii
 
 
-def _legacy(name):
-    def fn(*a, **k):
-        raise NotImplementedError(
-            f"diff_gaussian_rasterization.{name} belongs to the reference's legacy (never called) tile-exchange path "
-            "(SURVEY.md section 8a rows L1-L4) and is not provided yet.")
-    fn.__name__ = name
-    return fn
-
-
-load_image_tiles_by_pos = _legacy("load_image_tiles_by_pos")
-merge_image_tiles_by_pos = _legacy("merge_image_tiles_by_pos")
+# legacy tile-exchange operators (module level in the reference's extension; loss_distribution.py:168-195)
+load_image_tiles_by_pos = _ops.load_image_tiles_by_pos
+merge_image_tiles_by_pos = _ops.merge_image_tiles_by_pos

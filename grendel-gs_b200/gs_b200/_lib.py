@@ -52,6 +52,13 @@ SIGNATURES = {
     "gs_xchg_unpack": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_xchg_pack_grad": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "gs_xchg_scatter_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gs_sparse_grad_mask": (_i, [_i, _vp, _vp, _vp]),
+    "gs_sparse_grad_pack": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "gs_sparse_grad_unpack": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "gs_get_touched_locally": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "gs_get_pixels_compute_locally_and_in_rect": (_i, [_i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "gs_image_tiles_gather": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "gs_image_tiles_scatter_add": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 

@@ -383,3 +383,100 @@ class _FusedL1SSIM(torch.autograd.Function):
 def fused_l1_ssim(image, gt_u8, row0, row1):
     """-> (Ll1, ssim_loss) 0-dim tensors, both normalised by 3*H*W of the FULL image."""
     return _FusedL1SSIM.apply(image, gt_u8, int(row0), int(row1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# legacy tile-mask / tile-exchange helpers (SURVEY.md 8a rows L3-L4; never called by the shipped trainer)
+# ---------------------------------------------------------------------------------------------------------
+def _mask_u8(m):
+    if not m.is_cuda:
+        raise ValueError("compute_locally must be a CUDA tensor")
+    m = m.contiguous()
+    return m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+
+
+def get_touched_locally(compute_locally, image_height, image_width, extension_distance):
+    """(TILE_Y, TILE_X) bool: tiles within `extension_distance` tiles of a locally computed tile
+    (/root/reference/gaussian_renderer/loss_distribution.py:136-141)."""
+    cl = _mask_u8(compute_locally)
+    ty, tx = (int(image_height) + BLOCK_Y - 1) // BLOCK_Y, (int(image_width) + BLOCK_X - 1) // BLOCK_X
+    if cl.numel() != ty * tx:
+        raise ValueError("compute_locally does not match the image's tile grid")
+    out = torch.empty((ty, tx), dtype=torch.bool, device=cl.device)
+    _lib.call("gs_get_touched_locally", ty, tx, int(extension_distance), cl.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def get_pixels_compute_locally_and_in_rect(compute_locally, image_height, image_width, min_y, max_y, min_x, max_x):
+    """(max_y-min_y, max_x-min_x) bool pixel mask: is the pixel's tile computed locally (loss_distribution.py:205-213)."""
+    cl = _mask_u8(compute_locally)
+    out = torch.empty((int(max_y) - int(min_y), int(max_x) - int(min_x)), dtype=torch.bool, device=cl.device)
+    _lib.call("gs_get_pixels_compute_locally_and_in_rect", int(image_height), int(image_width), cl.data_ptr(), int(min_y),
+              int(max_y), int(min_x), int(max_x), out.data_ptr(), _stream())
+    return out
+
+
+class _LoadImageTilesByPos(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rect, pos, H, W, pixels_rect, tiles_rect):
+        rect = _f32c(rect, "local_image_rect")
+        pos = pos.to(device=rect.device, dtype=torch.int64).contiguous().reshape(-1, 2)
+        n = pos.shape[0]
+        _, rh, rw = rect.shape
+        tiles = torch.empty((n, 3, BLOCK_Y, BLOCK_X), dtype=torch.float32, device=rect.device)
+        _lib.call("gs_image_tiles_gather", n, pos.data_ptr(), rect.data_ptr(), rh, rw, int(pixels_rect[0]),
+                  int(pixels_rect[2]), int(H), int(W), tiles.data_ptr(), _stream())
+        ctx.save_for_backward(pos)
+        ctx.meta = (rh, rw, int(pixels_rect[0]), int(pixels_rect[2]), int(H), int(W))
+        return tiles
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        rh, rw, y0, x0, H, W = ctx.meta
+        g = _f32c(g, "grad")
+        out = torch.zeros((3, rh, rw), dtype=torch.float32, device=g.device)
+        _lib.call("gs_image_tiles_scatter_add", pos.shape[0], pos.data_ptr(), g.data_ptr(), rh, rw, y0, x0, H, W,
+                  out.data_ptr(), _stream())
+        return out, None, None, None, None, None
+
+
+class _MergeImageTilesByPos(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, tiles, H, W, pixels_rect, tiles_rect):
+        tiles = _f32c(tiles, "tiles")
+        pos = pos.to(device=tiles.device, dtype=torch.int64).contiguous().reshape(-1, 2)
+        rh, rw = int(pixels_rect[1]) - int(pixels_rect[0]), int(pixels_rect[3]) - int(pixels_rect[2])
+        out = torch.zeros((3, rh, rw), dtype=torch.float32, device=tiles.device)
+        _lib.call("gs_image_tiles_scatter_add", pos.shape[0], pos.data_ptr(), tiles.data_ptr(), rh, rw,
+                  int(pixels_rect[0]), int(pixels_rect[2]), int(H), int(W), out.data_ptr(), _stream())
+        ctx.save_for_backward(pos)
+        ctx.meta = (rh, rw, int(pixels_rect[0]), int(pixels_rect[2]), int(H), int(W))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        rh, rw, y0, x0, H, W = ctx.meta
+        g = _f32c(g, "grad")
+        n = pos.shape[0]
+        tiles = torch.empty((n, 3, BLOCK_Y, BLOCK_X), dtype=torch.float32, device=g.device)
+        _lib.call("gs_image_tiles_gather", n, pos.data_ptr(), g.data_ptr(), rh, rw, y0, x0, H, W, tiles.data_ptr(),
+                  _stream())
+        return None, tiles, None, None, None, None
+
+
+def load_image_tiles_by_pos(local_image_rect, all_pos_send_to_j, image_height, image_width, touched_pixels_rect,
+                            touched_tiles_rect):
+    """(3,h,w) local rect -> (n,3,16,16) tiles at GLOBAL tile positions (n,2); differentiable
+    (/root/reference/gaussian_renderer/loss_distribution.py:168-175)."""
+    return _LoadImageTilesByPos.apply(local_image_rect, all_pos_send_to_j, image_height, image_width,
+                                      touched_pixels_rect, touched_tiles_rect)
+
+
+def merge_image_tiles_by_pos(all_pos_recv_from_i, all_tiles_recv_from_i, image_height, image_width, touched_pixels_rect,
+                             touched_tiles_rect):
+    """(n,3,16,16) tiles at GLOBAL tile positions -> (3,h,w) local rect, zero elsewhere; differentiable
+    (loss_distribution.py:188-195)."""
+    return _MergeImageTilesByPos.apply(all_pos_recv_from_i, all_tiles_recv_from_i, image_height, image_width,
+                                       touched_pixels_rect, touched_tiles_rect)

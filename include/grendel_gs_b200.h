@@ -238,6 +238,37 @@ GS_API int gs_xchg_scatter_grad(int B, int P, int W, const uint8_t *flags, const
                                 void *const *d_means2D_ptrs_host, void *const *d_rgb_ptrs_host,
                                 void *const *d_conic_opacity_ptrs_host, void *stream);
 
+/* ---- sparse per-Gaussian gradient all-reduce staging (replicated Gaussians) ----------------------------------
+ * /root/reference/scene/gaussian_model.py:1332-1391 (get_sparse_ids, sync_gradients_sparsely) and the
+ * "fused_sparse" mode it leaves NotImplemented (:1438-1439).  mask[i] = _xyz.grad row i is non-zero; after an
+ * all-reduce(MAX) of the mask and gs_route_scan(ncols = 1), pack writes one 59-float row per touched Gaussian
+ * (xyz 3, features_dc 3, features_rest 45, scaling 3, rotation 4, opacity 1) for ONE all-reduce(SUM); unpack
+ * scatters the sums back.  grads_host: HOST array of the six device gradient pointers in that order. */
+GS_API int gs_sparse_grad_mask(int P, const float *xyz_grad, uint8_t *mask, void *stream);
+GS_API int gs_sparse_grad_pack(int P, const uint8_t *mask, const int32_t *pos, void *const *grads_host, float *rows,
+                               void *stream);
+GS_API int gs_sparse_grad_unpack(int P, const uint8_t *mask, const int32_t *pos, const float *rows,
+                                 void *const *grads_host, void *stream);
+
+/* ---- legacy tile-mask / tile-exchange helpers (dead code in the shipped trainer) ------
+ * _C.get_touched_locally                     -- gaussian_renderer/loss_distribution.py:136-141
+ * _C.get_pixels_compute_locally_and_in_rect  -- loss_distribution.py:205-213
+ * load_image_tiles_by_pos / merge_image_tiles_by_pos (forward of one is the adjoint of the other)
+ *                                            -- loss_distribution.py:168-175, 188-195
+ * masks are uint8/bool; pos is (n,2) int64 GLOBAL tile (y,x); image_rect is (3,rect_h,rect_w) whose pixel (0,0) is
+ * image pixel (rect_min_y, rect_min_x); tiles is (n,3,16,16). */
+GS_API int gs_get_touched_locally(int tile_y, int tile_x, int extension_distance, const uint8_t *compute_locally,
+                                  uint8_t *out, void *stream);
+GS_API int gs_get_pixels_compute_locally_and_in_rect(int image_height, int image_width, const uint8_t *compute_locally,
+                                                     int min_y, int max_y, int min_x, int max_x, uint8_t *out,
+                                                     void *stream);
+GS_API int gs_image_tiles_gather(int n, const int64_t *pos, const float *image_rect, int rect_h, int rect_w,
+                                 int rect_min_y, int rect_min_x, int image_height, int image_width, float *tiles,
+                                 void *stream);
+GS_API int gs_image_tiles_scatter_add(int n, const int64_t *pos, const float *tiles, int rect_h, int rect_w,
+                                      int rect_min_y, int rect_min_x, int image_height, int image_width,
+                                      float *image_rect, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,26 @@ def main():
             print(f"[mgpu] grad {n}: rms {rms:.3e} max_abs_err {np.abs(a - b).max():.3e} outside tol {badf:.1e}")
             assert badf <= 1e-3, n
         print("[mgpu] PASS world_size", world)
+
+    # ---- 3. replicated-Gaussian gradient sync: fused sparse all-reduce == dense all-reduce -------------------
+    from gs_b200 import grad_sync
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    P2 = 20011
+    shapes = [(P2, 3), (P2, 1, 3), (P2, 15, 3), (P2, 3), (P2, 4), (P2, 1)]
+    touched = torch.rand((P2,), device=dev, generator=g) < 0.07     # each rank touches ~7 % of the Gaussians
+    params_a, params_b = [], []
+    for shp in shapes:
+        grad = torch.randn(shp, device=dev, generator=g)
+        grad[~touched] = 0
+        pa, pb = torch.zeros(shp, device=dev), torch.zeros(shp, device=dev)
+        pa.grad, pb.grad = grad.clone(), grad.clone()
+        params_a.append(pa); params_b.append(pb)
+    n_touched = grad_sync.sync_gradients_fused_sparse(params_a)
+    grad_sync.sync_gradients_densely(params_b)
+    for pa, pb in zip(params_a, params_b):
+        assert torch.allclose(pa.grad, pb.grad, rtol=1e-6, atol=1e-6), "fused sparse gradient sync != dense all-reduce"
+    if rank == 0:
+        print(f"[mgpu] fused sparse gradient all-reduce: {n_touched} of {P2} Gaussians touched, matches dense all-reduce")
     dist.barrier()
     dist.destroy_process_group()
 

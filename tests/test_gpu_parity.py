@@ -305,3 +305,40 @@ def test_whole_step_parity_fused_path(o32):
     g_rot = gq - q * (q * gq).sum(1, keepdims=True)   # |q| = 1
     frac, _ = gu.rel_report("fusedstep.rotation", gu.npy(p._rotation.grad), g_rot)
     assert frac <= 5 * OUTLIER_FRAC
+
+
+def test_legacy_tile_helpers_match_plain_torch():
+    """Rows L3/L4: tile-mask dilation, pixel mask crop, tile gather / scatter and their autograd."""
+    import diff_gaussian_rasterization as dgr
+    H, W = 150, 211
+    ty, tx = 10, 14
+    g = torch.Generator(device="cuda").manual_seed(3)
+    cl = torch.rand((ty, tx), device="cuda", generator=g) < 0.3
+    touched = dgr._C.get_touched_locally(cl, H, W, 1)
+    ref = torch.nn.functional.max_pool2d(cl[None, None].float(), 3, 1, 1)[0, 0] > 0
+    assert touched.dtype == torch.bool and torch.equal(touched, ref)
+    y0, y1, x0, x1 = 16, 112, 32, 160
+    pm = dgr._C.get_pixels_compute_locally_and_in_rect(cl, H, W, y0, y1, x0, x1)
+    full = cl.repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W]
+    assert torch.equal(pm, full[y0:y1, x0:x1])
+    # tiles inside the rect (tile rows 1..6, cols 2..9), one on the ragged image edge
+    pos = torch.tensor([[1, 2], [3, 5], [6, 9], [4, 2]], dtype=torch.int64, device="cuda")
+    rect = torch.randn((3, y1 - y0, x1 - x0), device="cuda", generator=g, requires_grad=True)
+    tiles = dgr.load_image_tiles_by_pos(rect, pos, H, W, [y0, y1, x0, x1], [1, 7, 2, 10])
+    exp = torch.stack([rect[:, (p[0] * 16 - y0):(p[0] * 16 - y0 + 16), (p[1] * 16 - x0):(p[1] * 16 - x0 + 16)] for p in pos.tolist()])
+    assert torch.equal(tiles, exp)
+    w = torch.randn_like(tiles)
+    (tiles * w).sum().backward()
+    gref = torch.zeros_like(rect)
+    for k, p in enumerate(pos.tolist()):
+        gref[:, (p[0] * 16 - y0):(p[0] * 16 - y0 + 16), (p[1] * 16 - x0):(p[1] * 16 - x0 + 16)] += w[k]
+    assert torch.allclose(rect.grad, gref)
+    t2 = torch.randn((4, 3, 16, 16), device="cuda", generator=g, requires_grad=True)
+    merged = dgr.merge_image_tiles_by_pos(pos, t2, H, W, [y0, y1, x0, x1], [1, 7, 2, 10])
+    mref = torch.zeros((3, y1 - y0, x1 - x0), device="cuda")
+    for k, p in enumerate(pos.tolist()):
+        mref[:, (p[0] * 16 - y0):(p[0] * 16 - y0 + 16), (p[1] * 16 - x0):(p[1] * 16 - x0 + 16)] = t2[k].detach()
+    assert torch.equal(merged, mref)
+    w2 = torch.randn_like(merged)
+    (merged * w2).sum().backward()
+    assert torch.allclose(t2.grad, torch.stack([w2[:, (p[0] * 16 - y0):(p[0] * 16 - y0 + 16), (p[1] * 16 - x0):(p[1] * 16 - x0 + 16)] for p in pos.tolist()]))
