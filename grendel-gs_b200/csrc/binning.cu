@@ -2,26 +2,36 @@
 // 50 (radix sort), 60 (tile ranges) of /root/reference/analyze_statistic.py:1976-1980, i.e. the
 // first half of GaussianRasterizer.render_gaussians (/root/reference/gaussian_renderer/__init__.py:1271).
 //
-// All of this is integer / byte work bound by HBM traffic.  The scan and the sort are CUB device
-// primitives (the reference's stages 30 and 50 are CUB calls too); the sort only touches the
-// 32 + ceil(log2 T) key bits that can differ.
+// All of this is integer / byte work bound by HBM traffic.  The scan and the sorts are CUB device
+// primitives (the reference's stages 30 and 50 are CUB calls too).
+//
+// The published algorithm sorts R (splat, tile) instances by the 64-bit key  tile << 32 | depth bits
+// (45 significant bits at 1080p = 6 onesweep passes over 12 B/instance; 0.385 ms at R = 5.7 M).  The same
+// order is produced here by two cheaper stable sorts:
+//   1. the P splats are sorted ONCE by their 32-bit depth key (culled splats get 0xFFFFFFFF), value = splat index;
+//   2. instances are emitted in that depth order with a 32-bit TILE key, and one stable radix sort over only the
+//      ceil(log2 T) tile bits (2 passes over 8 B/instance) groups them by tile.
+// A stable sort by depth followed by a stable sort by tile IS the stable sort by (tile, depth): the sorted id
+// list, the tile ranges and hence the blend order are identical to the 64-bit sort, entry for entry
+// (tests/test_gpu_parity.py::test_tile_binning_bit_exact rebuilds the 64-bit keys and compares with the oracle).
 #include <cub/cub.cuh>
 
 #include "common.cuh"
 
 #define BIN_THREADS 256
+#define GS_THR_MARGIN 0.02f
 
-// Stages 21-24: per-splat number of LOCAL tiles its rectangle touches + the packed 48-byte record the
-// blend kernels gather:
+// Stages 21-24: per-splat number of LOCAL tiles its rectangle touches, its depth sort key, and the packed
+// 48-byte record the blend kernels gather:
 //   r0 = (mx, my, a', b')      a' = -A/2, b' = -B, c' = -C/2  so that  power = a'dx^2 + b'dx dy + c'dy^2
 //   r1 = (c', opacity, thr, red)     thr = ln(1/(255*opacity)) - margin: power < thr  =>  alpha < 1/255
 //   r2 = (green, blue, ex, ey)       half extents of the bounding box of {power >= thr} (+0.5 px slack),
-//                                    used by the blend kernels to cull splats per 4x4 pixel block
-#define GS_THR_MARGIN 0.02f
+//                                    used by the blend kernels to cull splats per 4x4 / 8x4 pixel block
 __global__ void __launch_bounds__(BIN_THREADS)
 k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const float *__restrict__ conic_opacity,
-              const float *__restrict__ rgb, const int32_t *__restrict__ radii,
-              const uint8_t *__restrict__ compute_locally, uint32_t *__restrict__ touched, float *__restrict__ rec) {
+              const float *__restrict__ rgb, const float *__restrict__ depths, const int32_t *__restrict__ radii,
+              const uint8_t *__restrict__ compute_locally, uint32_t *__restrict__ touched,
+              uint32_t *__restrict__ depth_key, uint32_t *__restrict__ index, float *__restrict__ rec) {
     const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
     if (i >= P) return;
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
@@ -37,6 +47,8 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
         }
     }
     touched[i] = n;
+    depth_key[i] = n > 0 ? __float_as_uint(depths[i]) : 0xffffffffu;  // depths are > 0.2: bits sort like values
+    index[i] = (uint32_t)i;
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     if (n > 0) {
         const float4 co = *reinterpret_cast<const float4 *>(conic_opacity + 4 * i);
@@ -60,79 +72,103 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
     o[0] = r0; o[1] = r1; o[2] = r2;
 }
 
-// Stage 40: one (tile << 32 | depth bits, splat id) pair per (splat, local tile), in splat order.
+// touched counts permuted into depth order (input of the inclusive scan that yields the instance offsets)
 __global__ void __launch_bounds__(BIN_THREADS)
-k_duplicate(int P, int W, int H, const float *__restrict__ means2D, const float *__restrict__ depths,
-            const int32_t *__restrict__ radii, const uint8_t *__restrict__ compute_locally,
-            const uint32_t *__restrict__ offsets, uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
-    const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
-    if (i >= P) return;
-    const int r = radii[i];
-    if (r <= 0) return;
-    uint32_t off = (i == 0) ? 0u : offsets[i - 1];
-    if (offsets[i] == off) return;
+k_gather_touched(int P, const uint32_t *__restrict__ order, const uint32_t *__restrict__ touched,
+                 uint32_t *__restrict__ touched_sorted) {
+    const int s = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (s < P) touched_sorted[s] = touched[order[s]];
+}
+
+// Stage 40: one (tile, splat id) pair per (splat, local tile), emitted in DEPTH order of the splats.
+__global__ void __launch_bounds__(BIN_THREADS)
+k_duplicate(int P, int W, int H, const float *__restrict__ means2D, const int32_t *__restrict__ radii,
+            const uint8_t *__restrict__ compute_locally, const uint32_t *__restrict__ order,
+            const uint32_t *__restrict__ offsets, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ ids) {
+    const int s = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (s >= P) return;
+    uint32_t off = (s == 0) ? 0u : offsets[s - 1];
+    if (offsets[s] == off) return;  // culled or no local tile
+    const uint32_t i = order[s];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
-    const float2 m = *reinterpret_cast<const float2 *>(means2D + 2 * i);
+    const float2 m = *reinterpret_cast<const float2 *>(means2D + 2 * (size_t)i);
     int x0, y0, x1, y1;
-    gs_get_rect(m.x, m.y, r, gx, gy, x0, y0, x1, y1);
-    const uint64_t dbits = (uint64_t)__float_as_uint(depths[i]);
+    gs_get_rect(m.x, m.y, radii[i], gx, gy, x0, y0, x1, y1);
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) {
             const int t = y * gx + x;
             if (!compute_locally[t]) continue;
-            keys[off] = ((uint64_t)(uint32_t)t << 32) | dbits;
-            ids[off] = (uint32_t)i;
+            tile_keys[off] = (uint32_t)t;
+            ids[off] = i;
             off++;
         }
 }
 
 // Stage 60: [start,end) of every tile in the sorted list.
 __global__ void __launch_bounds__(BIN_THREADS)
-k_tile_ranges(int64_t R, const uint64_t *__restrict__ keys, uint32_t *__restrict__ ranges) {
+k_tile_ranges(int64_t R, const uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ ranges) {
     const int64_t k = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x;
     if (k >= R) return;
-    const uint32_t t = (uint32_t)(keys[k] >> 32);
-    if (k == 0 || t != (uint32_t)(keys[k - 1] >> 32)) ranges[2 * t] = (uint32_t)k;
-    if (k == R - 1 || t != (uint32_t)(keys[k + 1] >> 32)) ranges[2 * t + 1] = (uint32_t)(k + 1);
+    const uint32_t t = tile_keys[k];
+    if (k == 0 || t != tile_keys[k - 1]) ranges[2 * t] = (uint32_t)k;
+    if (k == R - 1 || t != tile_keys[k + 1]) ranges[2 * t + 1] = (uint32_t)(k + 1);
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static size_t count_cub_bytes(int P) {
+    size_t scan = 0, sort = 0;
+    const int n = P > 0 ? P : 1;
+    cub::DeviceScan::InclusiveSum(nullptr, scan, (const uint32_t *)nullptr, (uint32_t *)nullptr, n);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 32);
+    return align_up(scan > sort ? scan : sort, 256);
+}
+
+// temp layout: 5 arrays of P uint32 (touched, depth_key, depth_key_sorted, index, touched_sorted) + CUB scratch
 extern "C" size_t gs_render_count_temp_bytes(int P) {
-    size_t scan = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, scan, (const uint32_t *)nullptr, (uint32_t *)nullptr, P > 0 ? P : 1);
-    return align_up((size_t)(P > 0 ? P : 1) * sizeof(uint32_t), 256) + align_up(scan, 256) + 256;
+    return 5 * align_up((size_t)(P > 0 ? P : 1) * sizeof(uint32_t), 256) + count_cub_bytes(P) + 256;
 }
 
 extern "C" int gs_render_count(int P, int image_height, int image_width, const float *means2D,
-                               const float *conic_opacity, const float *rgb, const int32_t *radii,
-                               const uint8_t *compute_locally, uint32_t *offsets, float *rec, void *temp,
-                               size_t temp_bytes, int64_t *R_host, void *stream_) {
+                               const float *conic_opacity, const float *rgb, const float *depths, const int32_t *radii,
+                               const uint8_t *compute_locally, uint32_t *order, uint32_t *offsets, float *rec,
+                               void *temp, size_t temp_bytes, int64_t *R_host, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GS_REQUIRE(P >= 0 && image_height > 0 && image_width > 0, "sizes");
     GS_REQUIRE(R_host != nullptr, "R_host");
     *R_host = 0;
     if (P == 0) return GS_OK;
-    GS_REQUIRE(means2D && conic_opacity && rgb && radii && compute_locally && offsets && rec && temp, "null pointer");
+    GS_REQUIRE(means2D && conic_opacity && rgb && depths && radii && compute_locally && order && offsets && rec && temp,
+               "null pointer");
     GS_REQUIRE(((uintptr_t)rec & 15) == 0 && ((uintptr_t)conic_opacity & 15) == 0 && ((uintptr_t)means2D & 7) == 0,
                "alignment");
     if (temp_bytes < gs_render_count_temp_bytes(P)) {
         gs_set_error("gs_render_count: temp too small (%zu < %zu)", temp_bytes, gs_render_count_temp_bytes(P));
         return GS_ENOMEM;
     }
-    uint32_t *touched = (uint32_t *)temp;
-    char *scan_temp = (char *)temp + align_up((size_t)P * sizeof(uint32_t), 256);
-    size_t scan_bytes = temp_bytes - align_up((size_t)P * sizeof(uint32_t), 256);
+    const size_t stride = align_up((size_t)P * sizeof(uint32_t), 256);
+    char *base = (char *)temp;
+    uint32_t *touched = (uint32_t *)base, *dkey = (uint32_t *)(base + stride), *dkey_sorted = (uint32_t *)(base + 2 * stride),
+             *index = (uint32_t *)(base + 3 * stride), *touched_sorted = (uint32_t *)(base + 4 * stride);
+    void *cub_temp = base + 5 * stride;
+    size_t cub_bytes = temp_bytes - 5 * stride;
     const int grid = (P + BIN_THREADS - 1) / BIN_THREADS;
     {
         GsStageTimer timer(GS_STAGE_COUNT_TILES, stream);
-        k_count_tiles<<<grid, BIN_THREADS, 0, stream>>>(P, image_width, image_height, means2D, conic_opacity, rgb, radii,
-                                                        compute_locally, touched, rec);
+        k_count_tiles<<<grid, BIN_THREADS, 0, stream>>>(P, image_width, image_height, means2D, conic_opacity, rgb, depths,
+                                                        radii, compute_locally, touched, dkey, index, rec);
         GS_LAUNCH_CHECK();
     }
     {
+        GsStageTimer timer(GS_STAGE_SORT, stream);  // depth order of the splats (stable: ties keep index order)
+        GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, dkey, dkey_sorted, index, order, P, 0, 32, stream));
+    }
+    {
         GsStageTimer timer(GS_STAGE_SCAN, stream);
-        GS_CUDA_TRY(cub::DeviceScan::InclusiveSum(scan_temp, scan_bytes, touched, offsets, P, stream));
+        k_gather_touched<<<grid, BIN_THREADS, 0, stream>>>(P, order, touched, touched_sorted);
+        GS_LAUNCH_CHECK();
+        GS_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_temp, cub_bytes, touched_sorted, offsets, P, stream));
     }
     uint32_t last = 0;
     GS_CUDA_TRY(cudaMemcpyAsync(&last, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -141,16 +177,16 @@ extern "C" int gs_render_count(int P, int image_height, int image_width, const f
     return GS_OK;
 }
 
-static int key_bits(int T) {
+static int tile_bits(int T) {
     int b = 0;
     while ((1ll << b) < (long long)T) b++;
-    return 32 + (b > 0 ? b : 1);
+    return b > 0 ? b : 1;
 }
 
 extern "C" size_t gs_render_sort_temp_bytes(int64_t R) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, R > 0 ? R : 1, 0, 64);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, R > 0 ? R : 1, 0, 32);
     return align_up(bytes, 256) + 256;
 }
 
@@ -160,20 +196,20 @@ int gs_launch_blend_forward(int64_t R, int H, int W, const float *rec, const flo
                             uint32_t *n_contrib, int64_t *stats, cudaStream_t stream);
 
 extern "C" int gs_render_forward(int P, int64_t R, int image_height, int image_width, const float *means2D,
-                                 const float *depths, const int32_t *radii, const uint8_t *compute_locally,
-                                 const uint32_t *offsets, const float *rec, const float *bg, uint64_t *keys_unsorted,
-                                 uint32_t *ids_unsorted, uint64_t *keys_sorted, uint32_t *ids_sorted, void *sort_temp,
+                                 const int32_t *radii, const uint8_t *compute_locally, const uint32_t *order,
+                                 const uint32_t *offsets, const float *rec, const float *bg, uint32_t *tiles_unsorted,
+                                 uint32_t *ids_unsorted, uint32_t *tiles_sorted, uint32_t *ids_sorted, void *sort_temp,
                                  size_t sort_temp_bytes, uint32_t *ranges, float *image, float *final_T,
                                  uint32_t *n_contrib, int64_t *stats, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GS_REQUIRE(P >= 0 && R >= 0 && image_height > 0 && image_width > 0, "sizes");
-    GS_REQUIRE(R < (1ll << 32), "more than 2^32 splat-tile instances");
+    GS_REQUIRE(R < (1ll << 31), "more than 2^31 splat-tile instances");
     GS_REQUIRE(compute_locally && bg && ranges && image && final_T && n_contrib, "null pointer");
     const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     const int T = gx * gy;
     GS_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * (size_t)T, stream));
     if (R > 0) {
-        GS_REQUIRE(means2D && depths && radii && offsets && rec && keys_unsorted && ids_unsorted && keys_sorted &&
+        GS_REQUIRE(means2D && radii && order && offsets && rec && tiles_unsorted && ids_unsorted && tiles_sorted &&
                        ids_sorted && sort_temp,
                    "null pointer");
         if (sort_temp_bytes < gs_render_sort_temp_bytes(R)) {
@@ -183,17 +219,17 @@ extern "C" int gs_render_forward(int P, int64_t R, int image_height, int image_w
         {
             GsStageTimer timer(GS_STAGE_DUPLICATE, stream);
             k_duplicate<<<(P + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, stream>>>(
-                P, image_width, image_height, means2D, depths, radii, compute_locally, offsets, keys_unsorted, ids_unsorted);
+                P, image_width, image_height, means2D, radii, compute_locally, order, offsets, tiles_unsorted, ids_unsorted);
             GS_LAUNCH_CHECK();
         }
         {
-            GsStageTimer timer(GS_STAGE_SORT, stream);
-            GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_unsorted, keys_sorted,
-                                                        ids_unsorted, ids_sorted, R, 0, key_bits(T), stream));
+            GsStageTimer timer(GS_STAGE_SORT, stream);  // stable sort on the tile bits only
+            GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, tiles_unsorted, tiles_sorted,
+                                                        ids_unsorted, ids_sorted, (int)R, 0, tile_bits(T), stream));
         }
         {
             GsStageTimer timer(GS_STAGE_RANGES, stream);
-            k_tile_ranges<<<(unsigned)((R + BIN_THREADS - 1) / BIN_THREADS), BIN_THREADS, 0, stream>>>(R, keys_sorted, ranges);
+            k_tile_ranges<<<(unsigned)((R + BIN_THREADS - 1) / BIN_THREADS), BIN_THREADS, 0, stream>>>(R, tiles_sorted, ranges);
             GS_LAUNCH_CHECK();
         }
     }

@@ -243,18 +243,19 @@ class _RenderGaussians(torch.autograd.Function):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         offsets = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
+        order = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
         rec = torch.empty((max(P, 1), 12), dtype=torch.float32, device=dev)
         tb = _lib.query("gs_render_count_temp_bytes", P)
         temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
         R = C.c_int64(0)
         _lib.call("gs_render_count", P, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
-                  radii.data_ptr(), cl.data_ptr(), offsets.data_ptr(), rec.data_ptr(), temp.data_ptr(), tb,
-                  C.byref(R), s)
+                  depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(),
+                  rec.data_ptr(), temp.data_ptr(), tb, C.byref(R), s)
         R = int(R.value)
         global LAST_R_TOTAL
         LAST_R_TOTAL += R
         Ra = max(R, 1)
-        keys = torch.empty((2, Ra), dtype=torch.int64, device=dev)
+        tiles = torch.empty((2, Ra), dtype=torch.int32, device=dev)
         ids = torch.empty((2, Ra), dtype=torch.int32, device=dev)
         sb = _lib.query("gs_render_sort_temp_bytes", R)
         sort_temp = torch.empty((sb,), dtype=torch.uint8, device=dev)
@@ -263,17 +264,15 @@ class _RenderGaussians(torch.autograd.Function):
         final_T = torch.empty((H, W), dtype=torch.float32, device=dev)
         n_contrib = torch.empty((H, W), dtype=torch.int32, device=dev)
         stats = torch.empty((3,), dtype=torch.int64, device=dev)
-        _lib.call("gs_render_forward", P, R, H, W, means2D.data_ptr(), depths.data_ptr(), radii.data_ptr(),
-                  cl.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), keys[0].data_ptr(),
-                  ids[0].data_ptr(), keys[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(),
+        _lib.call("gs_render_forward", P, R, H, W, means2D.data_ptr(), radii.data_ptr(), cl.data_ptr(),
+                  order.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), tiles[0].data_ptr(),
+                  ids[0].data_ptr(), tiles[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(),
                   image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), s)
         ev1.record()
         _timed(collector, "forward_render_time", ev0, ev1)
         ids_sorted = ids[1].clone() if R > 0 else ids[1]  # let the 2R-entry scratch go back to the allocator
         ctx.rs, ctx.R, ctx.P, ctx.collector = rs, R, P, collector
         ctx.save_for_backward(rec, bg, cl, ranges, ids_sorted, final_T, n_contrib)
-        ctx.debug = dict(keys_sorted=keys[1], ids_sorted=ids_sorted, ranges=ranges, offsets=offsets, R=R) \
-            if os.environ.get("GS_B200_KEEP_BINNING") == "1" else None
         n_render, n_consider, n_contrib_sum = stats[0], stats[1], stats[2]
         ctx.mark_non_differentiable(n_render, n_consider, n_contrib_sum)
         return image, n_render, n_consider, n_contrib_sum

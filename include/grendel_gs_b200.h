@@ -113,34 +113,41 @@ GS_API int gs_get_local2j_ids_bool_rects(int P, int image_height, int image_widt
 
 /* ---- GaussianRasterizer.render_gaussians -- gaussian_renderer/__init__.py:1271-1282 -------------
  * Three calls because the number R of (splat, local tile) instances is data dependent:
- *   gs_render_count   stages 21-24 + 30: per-splat LOCAL tile count, inclusive scan, packed records
+ *   gs_render_count   stages 21-24 + 30: per-splat LOCAL tile count, depth order of the splats, inclusive scan,
+ *                     packed records
  *   gs_render_forward stages 40,50,60,70,81-83: duplicate-with-keys, radix sort, tile ranges, blend
  *   gs_render_backward stage b10
+ * The sorted instance list is the one the published 64-bit sort (key = tile << 32 | fp32 depth bits, stable)
+ * produces; it is obtained as a stable 32-bit depth sort of the P splats followed by a stable sort of the R
+ * instances on their tile bits only (see csrc/binning.cu).
  */
 
 /* Bytes of scratch gs_render_count needs for P splats. */
 GS_API size_t gs_render_count_temp_bytes(int P);
 
 /* compute_locally: (TILE_Y*TILE_X) uint8/bool mask (workload_division.py:773-787).
- * offsets: (P) uint32 inclusive prefix sum of local tiles touched.
+ * order: (P) uint32 splat indices in ascending depth (splats without a local tile last).
+ * offsets: (P) uint32 inclusive prefix sum of local tiles touched, IN THAT ORDER.
  * rec: (P, GS_REC_FLOATS) packed per-splat records consumed by the blend kernels.
  * R_host: HOST pointer; receives the instance count.  This call synchronises `stream`. */
 GS_API int gs_render_count(int P, int image_height, int image_width, const float *means2D, const float *conic_opacity,
-                    const float *rgb, const int32_t *radii, const uint8_t *compute_locally, uint32_t *offsets,
-                    float *rec, void *temp, size_t temp_bytes, int64_t *R_host, void *stream);
+                           const float *rgb, const float *depths, const int32_t *radii, const uint8_t *compute_locally,
+                           uint32_t *order, uint32_t *offsets, float *rec, void *temp, size_t temp_bytes,
+                           int64_t *R_host, void *stream);
 
 /* Bytes of radix-sort scratch for R instances. */
 GS_API size_t gs_render_sort_temp_bytes(int64_t R);
 
-/* keys_unsorted/keys_sorted: (R) uint64 = tile id << 32 | fp32 depth bits; ids_unsorted/ids_sorted: (R) uint32.
+/* tiles_unsorted/tiles_sorted: (R) uint32 tile ids; ids_unsorted/ids_sorted: (R) uint32 splat ids.
  * ranges: (T,2) uint32 [start,end) per tile.  bg: (3).  image: (3,H,W) -- written in full: non-local
  * tiles are exactly 0 (loss_distribution.py:1875).  final_T (H,W) f32 and n_contrib (H,W) uint32 are
  * kept for the backward.  stats: optional (3) int64 sums of n_render / n_consider / n_contrib, or NULL. */
-GS_API int gs_render_forward(int P, int64_t R, int image_height, int image_width, const float *means2D, const float *depths,
-                      const int32_t *radii, const uint8_t *compute_locally, const uint32_t *offsets, const float *rec,
-                      const float *bg, uint64_t *keys_unsorted, uint32_t *ids_unsorted, uint64_t *keys_sorted,
-                      uint32_t *ids_sorted, void *sort_temp, size_t sort_temp_bytes, uint32_t *ranges, float *image,
-                      float *final_T, uint32_t *n_contrib, int64_t *stats, void *stream);
+GS_API int gs_render_forward(int P, int64_t R, int image_height, int image_width, const float *means2D,
+                             const int32_t *radii, const uint8_t *compute_locally, const uint32_t *order,
+                             const uint32_t *offsets, const float *rec, const float *bg, uint32_t *tiles_unsorted,
+                             uint32_t *ids_unsorted, uint32_t *tiles_sorted, uint32_t *ids_sorted, void *sort_temp,
+                             size_t sort_temp_bytes, uint32_t *ranges, float *image, float *final_T,
+                             uint32_t *n_contrib, int64_t *stats, void *stream);
 
 /* dL_dimage: (3,H,W).  The three gradient outputs (P,2) (P,4) (P,3) are zero-filled and
  * accumulated by this call. */

@@ -65,16 +65,17 @@ def render_forward(H, W, means2D, conic_opacity, rgb, depths, radii, compute_loc
     cl = compute_locally.to(torch.uint8).contiguous()
     bg_t = to_dev(np.asarray(bg, np.float32))
     offsets = torch.empty((max(P, 1),), dtype=torch.int32, device=DEV)
+    order = torch.empty((max(P, 1),), dtype=torch.int32, device=DEV)
     rec = torch.empty((max(P, 1), 12), dtype=torch.float32, device=DEV)
     tb = _lib.query("gs_render_count_temp_bytes", P)
     temp = torch.empty((tb,), dtype=torch.uint8, device=DEV)
     R = C.c_int64(0)
     _lib.call("gs_render_count", P, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
-              radii.data_ptr(), cl.data_ptr(), offsets.data_ptr(), rec.data_ptr(), temp.data_ptr(), tb, C.byref(R),
-              stream())
+              depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(), rec.data_ptr(),
+              temp.data_ptr(), tb, C.byref(R), stream())
     R = int(R.value)
     Ra = max(R, 1)
-    keys = torch.zeros((2, Ra), dtype=torch.int64, device=DEV)
+    tiles = torch.zeros((2, Ra), dtype=torch.int32, device=DEV)
     ids = torch.zeros((2, Ra), dtype=torch.int32, device=DEV)
     sb = _lib.query("gs_render_sort_temp_bytes", R)
     sort_temp = torch.empty((sb,), dtype=torch.uint8, device=DEV)
@@ -83,12 +84,16 @@ def render_forward(H, W, means2D, conic_opacity, rgb, depths, radii, compute_loc
     final_T = torch.zeros((H, W), device=DEV)
     n_contrib = torch.zeros((H, W), dtype=torch.int32, device=DEV)
     stats = torch.zeros((3,), dtype=torch.int64, device=DEV)
-    _lib.call("gs_render_forward", P, R, H, W, means2D.data_ptr(), depths.data_ptr(), radii.data_ptr(), cl.data_ptr(),
-              offsets.data_ptr(), rec.data_ptr(), bg_t.data_ptr(), keys[0].data_ptr(), ids[0].data_ptr(),
-              keys[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(), image.data_ptr(),
+    _lib.call("gs_render_forward", P, R, H, W, means2D.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(),
+              offsets.data_ptr(), rec.data_ptr(), bg_t.data_ptr(), tiles[0].data_ptr(), ids[0].data_ptr(),
+              tiles[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(), image.data_ptr(),
               final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), stream())
     torch.cuda.synchronize()
-    return dict(R=R, offsets=offsets, rec=rec, keys=keys[1][:R], ids=ids[1][:R], ids_buf=ids[1], ranges=ranges,
+    # the 64-bit keys of the published algorithm, rebuilt from the sorted (tile, splat id) pairs
+    ids_s, tiles_s = ids[1][:R].to(torch.int64) & 0xffffffff, tiles[1][:R].to(torch.int64) & 0xffffffff
+    dbits = depths.view(torch.int32).to(torch.int64) & 0xffffffff
+    keys = (tiles_s << 32) | dbits[ids_s] if R > 0 else torch.zeros((0,), dtype=torch.int64, device=DEV)
+    return dict(R=R, offsets=offsets, order=order, rec=rec, keys=keys, ids=ids[1][:R], ids_buf=ids[1], ranges=ranges,
                 image=image, final_T=final_T, n_contrib=n_contrib, stats=stats, cl=cl, bg=bg_t, P=P, H=H, W=W)
 
 

@@ -78,7 +78,11 @@ def test_tile_binning_bit_exact(o32, n, W, H, rad):
         f = gu.render_forward(H, W, gu.to_dev(ref["means2D"]), gu.to_dev(ref["conic_opacity"]), gu.to_dev(ref["rgb"]),
                               gu.to_dev(ref["depths"]), gu.to_dev(ref["radii"]), gu.to_dev(cl), (0, 0, 0))
         assert f["R"] == rf["R"]
-        assert np.array_equal(gu.npy(f["offsets"]).view(np.uint32)[:n], rf["offsets"])
+        # splats in ascending depth (stable), those without a local tile last; offsets are the scan in that order
+        order = gu.npy(f["order"]).view(np.uint32)[:n]
+        dkey = np.where(rf["tiles_touched"] > 0, ref["depths"].view(np.uint32), np.uint32(0xffffffff))
+        assert np.array_equal(order, np.argsort(dkey, kind="stable").astype(np.uint32))
+        assert np.array_equal(gu.npy(f["offsets"]).view(np.uint32)[:n], np.cumsum(rf["tiles_touched"][order]).astype(np.uint32))
         assert np.array_equal(gu.npy(f["keys"]).view(np.uint64), rf["keys"])
         assert np.array_equal(gu.npy(f["ids"]).view(np.uint32), rf["ids"])
         assert np.array_equal(gu.npy(f["ranges"]).view(np.uint32), rf["ranges"])
