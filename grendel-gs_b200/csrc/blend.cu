@@ -18,12 +18,14 @@
 //     reach MUFU.EX2; finished / out-of-image pixels carry NaN coordinates so they fail it for free;
 //   * sorted splat ids are turned into 48-byte packed records (3 x float4, built by k_count_tiles), gathered
 //     once per (splat, tile) into shared memory;
-//   * backward: per-pixel weight m = dL/dG * G; its six moments (sum m, m dx, m dy, m dx^2, m dx dy, m dy^2) and
-//     three colour sums are reduced over the 16 lanes of the block by a 9-value transposing butterfly
-//     (12 shuffles instead of 36), stored in per-block private shared-memory slots (no shared atomics: sm_100
-//     has no native fp32 ATOMS.ADD -- it compiles to a CAS loop), then ONE thread per splat sums the blocks,
-//     applies the splat's constants and issues ONE set of 9 global RED.ADD per (splat, tile) -- instead of
-//     9 atomics per (splat, pixel) in the classical design.
+//   * backward (one 8x4 block per full warp, see the note above k_blend_bwd): per-pixel weight m = dL/dG * G; its
+//     six moments (sum m, m dx, m dy, m dx^2, m dx dy, m dy^2) and three colour sums are reduced over the warp by a
+//     9-value transposing butterfly (14 shuffles instead of 45), stored in per-warp private shared-memory slots
+//     (no shared atomics: sm_100 has no native fp32 ATOMS.ADD -- it compiles to a CAS loop), then ONE thread per
+//     splat sums the warps, applies the splat's constants and issues ONE set of 9 global RED.ADD per
+//     (splat, tile) -- instead of 9 atomics per (splat, pixel) in the classical design.  The per-pixel state is
+//     just (T, behind-colour B): lanes that skip a splat run the same instructions with alpha = 0, which makes
+//     every update a no-op, so the blend path has no per-lane branches or conditional moves.
 #include "common.cuh"
 
 #define BL_THREADS 256
@@ -294,18 +296,21 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
         __syncthreads();
         if ((uint32_t)base < wlast) {
             for (int g0 = (cnt - 1) & ~31; g0 >= 0; g0 -= 32) {
-                const int jj = g0 + lane;
+                // lane l inspects entry g0 + 31 - l, so the LOWEST set bit of the ballot is the DEEPEST candidate and
+                // the walk (back to front) pops bits with the cheap x & (x - 1)
+                const int jj = g0 + 31 - lane;
                 uint32_t cand = __ballot_sync(0xffffffffu, jj < cnt && ((s_cull[jj] >> warp) & 1));
                 uint32_t mybits = 0u;
+                const int last_rel = (int)last - base;  // entry j of this chunk is live for this pixel iff j < last_rel
                 while (cand) {
-                    const int b31 = 31 - __clz(cand);
+                    const int b31 = 32 - __ffs(cand);   // = 31 - (index of the lowest set bit)
                     const int j = g0 + b31;
-                    cand &= ~(1u << b31);
+                    cand &= cand - 1u;
                     const SRec *sr = &s_rec[j];
                     const float4 a = sr->a, b = sr->b;
                     const float dx = a.x - pxf, dy = a.y - pyf;
                     const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
-                    bool ok = ((uint32_t)(base + j) < last) && power >= b.z;
+                    bool ok = (j < last_rel) && power >= b.z;
                     if (!__any_sync(0xffffffffu, ok)) continue;
                     const float G = gs_exp_neg(power);
                     const float alpha = fminf(ALPHA_MAX, b.y * G);
