@@ -59,8 +59,34 @@ class ClockSampler:
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nvml, self.samples, self._stop = None, [], False
+
+    def _nvml_loop(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.gpu)
+        smax = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        while not self._stop:
+            try:
+                try:
+                    reasons = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), smax, reasons))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        # In-process NVML polling: spawning nvidia-smi inside the timed region stalls the driver for ~100 ms on an
+        # 8-GPU box (measured: 18.0 vs 5.6 ms/step), which would be charged to the step.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            threading.Thread(target=self._nvml_loop, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -74,6 +100,15 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            time.sleep(0.03)
+            bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            reasons = sorted({name for _, _, r in self.samples for b, name in bits.items() if r & b})
+            sm = [s[0] for s in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None,
+                    "sm_max_mhz": float(self.samples[0][1]) if self.samples else None, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

@@ -85,6 +85,9 @@ struct Proj {
     float a, b, c, det;
 };
 
+// COV_READY: o.L / o.S (camera independent) were filled by the caller -- the batched kernels compute them once per
+// splat and project it into B cameras.
+template <bool COV_READY = false>
 GS_D bool project(const Cam &cam, const float3 p, const float3 sc, float mod, const float4 q, float fx, float fy,
                   float tanfovx, float tanfovy, Proj &o) {
     const float *V = cam.V, *PM = cam.PM;
@@ -96,7 +99,7 @@ GS_D bool project(const Cam &cam, const float3 p, const float3 sc, float mod, co
     o.hy = PM[1] * p.x + PM[5] * p.y + PM[9] * p.z + PM[13];
     o.hw = PM[3] * p.x + PM[7] * p.y + PM[11] * p.z + PM[15];
     o.pw = 1.0f / (o.hw + 0.0000001f);
-    cov3d_from(sc, mod, q, o.L, o.S);
+    if (!COV_READY) cov3d_from(sc, mod, q, o.L, o.S);
     const float limx = 1.3f * tanfovx, limy = 1.3f * tanfovy;
     const float txtz = o.tx / o.tz, tytz = o.ty / o.tz;
     o.cx = fminf(limx, fmaxf(-limx, txtz)) * o.tz;

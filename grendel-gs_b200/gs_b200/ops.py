@@ -479,3 +479,72 @@ def merge_image_tiles_by_pos(all_pos_recv_from_i, all_tiles_recv_from_i, image_h
     (loss_distribution.py:188-195)."""
     return _MergeImageTilesByPos.apply(all_pos_recv_from_i, all_tiles_recv_from_i, image_height, image_width,
                                        touched_pixels_rect, touched_tiles_rect)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batched preprocess: all B cameras of a step in one launch
+# ---------------------------------------------------------------------------------------------------------
+def pack_cameras(settings_list):
+    """(B,40) float32 device tensor: viewmatrix[16], projmatrix[16], campos[3], tanfovx, tanfovy, 3 pad per camera."""
+    rows = []
+    for rs in settings_list:
+        dev = rs.viewmatrix.device
+        tail = torch.tensor([float(rs.tanfovx), float(rs.tanfovy), 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        rows.append(torch.cat([rs.viewmatrix.reshape(-1).float(), rs.projmatrix.reshape(-1).float(),
+                               rs.campos.reshape(-1).float(), tail]))
+    return torch.stack(rows).contiguous()
+
+
+class _PreprocessBatched(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, f_dc, f_rest, scaling, rotation, opacity, cams, meta):
+        xyz, f_dc, f_rest = _f32c(xyz, "_xyz"), _f32c(f_dc, "_features_dc"), _f32c(f_rest, "_features_rest")
+        scaling, rotation, opacity = _f32c(scaling, "_scaling"), _f32c(rotation, "_rotation"), _f32c(opacity, "_opacity")
+        cams = _f32c(cams, "cams")
+        P, B = xyz.shape[0], cams.shape[0]
+        if tuple(f_dc.shape) != (P, 1, 3) or tuple(f_rest.shape) != (P, 15, 3) or cams.shape[1] != 40:
+            raise ValueError("features must be (P,1,3)/(P,15,3) and cams (B,40)")
+        W, H, D, mod = meta
+        dev = xyz.device
+        means2D = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((B, P), dtype=torch.float32, device=dev)
+        radii = torch.empty((B, P), dtype=torch.int32, device=dev)
+        conic_opacity = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+        rgb = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
+        clamped = torch.empty((B, P), dtype=torch.uint8, device=dev)
+        _lib.call("gs_preprocess_forward_batched", B, P, int(D), xyz.data_ptr(), f_dc.data_ptr(), f_rest.data_ptr(),
+                  scaling.data_ptr(), float(mod), rotation.data_ptr(), opacity.data_ptr(), cams.data_ptr(), int(W),
+                  int(H), means2D.data_ptr(), depths.data_ptr(), radii.data_ptr(), conic_opacity.data_ptr(),
+                  rgb.data_ptr(), clamped.data_ptr(), _stream())
+        ctx.meta = meta
+        ctx.save_for_backward(xyz, f_dc, f_rest, scaling, rotation, opacity, cams, radii, clamped)
+        ctx.mark_non_differentiable(radii, depths)
+        return means2D, rgb, conic_opacity, radii, depths
+
+    @staticmethod
+    def backward(ctx, g_means2D, g_rgb, g_conic_opacity, _g_radii, _g_depths):
+        xyz, f_dc, f_rest, scaling, rotation, opacity, cams, radii, clamped = ctx.saved_tensors
+        W, H, D, mod = ctx.meta
+        P, B = xyz.shape[0], cams.shape[0]
+        dev = xyz.device
+
+        def z(g, shape):
+            return torch.zeros(shape, dtype=torch.float32, device=dev) if g is None else _f32c(g, "grad")
+
+        g_means2D, g_rgb, g_conic_opacity = z(g_means2D, (B, P, 2)), z(g_rgb, (B, P, 3)), z(g_conic_opacity, (B, P, 4))
+        d = [torch.empty_like(t) for t in (xyz, f_dc, f_rest, scaling, rotation, opacity)]
+        _lib.call("gs_preprocess_backward_batched", B, P, int(D), xyz.data_ptr(), f_dc.data_ptr(), f_rest.data_ptr(),
+                  scaling.data_ptr(), float(mod), rotation.data_ptr(), opacity.data_ptr(), cams.data_ptr(), int(W),
+                  int(H), radii.data_ptr(), clamped.data_ptr(), g_means2D.data_ptr(), g_conic_opacity.data_ptr(),
+                  g_rgb.data_ptr(), d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(),
+                  d[5].data_ptr(), _stream())
+        return d[0], d[1], d[2], d[3], d[4], d[5], None, None
+
+
+def preprocess_gaussians_batched(xyz, features_dc, features_rest, scaling, rotation, opacity, cams, image_width,
+                                 image_height, sh_degree, scale_modifier=1.0):
+    """All B cameras at once from the RAW GaussianModel parameters.  cams: pack_cameras(...) (B,40).
+    -> (means2D (B,P,2), rgb (B,P,3), conic_opacity (B,P,4), radii (B,P) int32, depths (B,P)); slice k equals the
+    single-camera operator's output for camera k."""
+    return _PreprocessBatched.apply(xyz, features_dc, features_rest, scaling, rotation, opacity, cams,
+                                    (int(image_width), int(image_height), int(sh_degree), float(scale_modifier)))

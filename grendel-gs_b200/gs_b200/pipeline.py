@@ -130,6 +130,7 @@ class Trainer:
         self.gts_dev = [g.to(device) for g in gts_pinned]   # copies for the "inputs resident" leg
         self.history = StrategyHistory([c.uid for c in self.dcams], self.tile_y, world)
         self._strip_cache = {}
+        self._cams_packed = None   # (B,40) camera table of the batched preprocess (cameras are fixed per Trainer)
         self._loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
         self._info = {}
         self._h2d = 0
@@ -180,8 +181,21 @@ class Trainer:
             xyz, scaling, rotation, feats, opacity = p.get_xyz, p.get_scaling, p.get_rotation, p.get_features, p.get_opacity
         collectors = [{} for _ in self.dcams]
         screen = []
-        V = 0
-        for k, rs in enumerate(settings):
+        if self.fused_activations and len(settings) > 1:
+            # all B cameras in ONE launch: every Gaussian is read once and projected into each camera
+            if self._cams_packed is None:
+                self._cams_packed = ops_.pack_cameras(settings)
+            bm2, brgb, bco, bradii, bdepths = ops_.preprocess_gaussians_batched(
+                p._xyz, p._features_dc, p._features_rest, p._scaling, p._rotation, p._opacity, self._cams_packed,
+                self.W, self.H, p.active_sh_degree)
+            for k in range(len(settings)):
+                m2 = bm2[k]
+                m2.retain_grad()
+                screen.append((m2, brgb[k], bco[k], bradii[k], bdepths[k]))
+            settings_loop = []
+        else:
+            settings_loop = settings
+        for k, rs in enumerate(settings_loop):
             if self.fused_activations:
                 out = ops_.preprocess_gaussians_raw(p._xyz, p._features_dc, p._features_rest, p._scaling, p._rotation,
                                                     p._opacity, rs)

@@ -101,6 +101,26 @@ GS_API int gs_preprocess_backward_raw(int P, int sh_degree, const float *xyz, co
                                       float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
                                       float *dL_dscaling, float *dL_drotation, float *dL_dopacity, void *stream);
 
+/* Batched fused-activation variants: ALL B cameras of a step (gaussian_renderer/__init__.py:919-963 loops over them
+ * in Python) in one launch; each Gaussian's parameters are read once and projected into every camera, and the
+ * backward accumulates the B cameras' contributions before writing each parameter gradient once.
+ * cams: (B,40) floats per camera = viewmatrix[16], projmatrix[16], campos[3], tanfovx, tanfovy, 3 pad; all cameras
+ * share image_width/height.  Outputs are (B,P,...) with camera k's slice identical to the single-camera result. */
+GS_API int gs_preprocess_forward_batched(int B, int P, int sh_degree, const float *xyz, const float *features_dc,
+                                         const float *features_rest, const float *scaling, float scale_modifier,
+                                         const float *rotation, const float *opacity, const float *cams,
+                                         int image_width, int image_height, float *means2D, float *depths,
+                                         int32_t *radii, float *conic_opacity, float *rgb, uint8_t *clamped,
+                                         void *stream);
+GS_API int gs_preprocess_backward_batched(int B, int P, int sh_degree, const float *xyz, const float *features_dc,
+                                          const float *features_rest, const float *scaling, float scale_modifier,
+                                          const float *rotation, const float *opacity, const float *cams,
+                                          int image_width, int image_height, const int32_t *radii,
+                                          const uint8_t *clamped, const float *dL_dmeans2D,
+                                          const float *dL_dconic_opacity, const float *dL_drgb, float *dL_dxyz,
+                                          float *dL_dfeatures_dc, float *dL_dfeatures_rest, float *dL_dscaling,
+                                          float *dL_drotation, float *dL_dopacity, void *stream);
+
 /* _C.get_local2j_ids_bool -- /root/reference/gaussian_renderer/workload_division.py:721-744.
  * strategy: (world_size+1) int32 ascending flattened tile ids; out: (P, world_size) uint8/bool. */
 GS_API int gs_get_local2j_ids_bool(int P, int image_height, int image_width, int world_size, const float *means2D,

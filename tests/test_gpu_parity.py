@@ -346,3 +346,37 @@ def test_legacy_tile_helpers_match_plain_torch():
     w2 = torch.randn_like(merged)
     (merged * w2).sum().backward()
     assert torch.allclose(t2.grad, torch.stack([w2[:, (p[0] * 16 - y0):(p[0] * 16 - y0 + 16), (p[1] * 16 - x0):(p[1] * 16 - x0 + 16)] for p in pos.tolist()]))
+
+
+def test_batched_preprocess_equals_per_camera():
+    """gs_preprocess_*_batched: slice k == single-camera raw operator (bitwise for the integer-deciding outputs),
+    and the accumulated parameter gradients match the sum of the per-camera backward passes."""
+    from gs_b200 import ops, pipeline
+    W, H, n, B = 320, 200, 20001, 3
+    sc = syn.make_scene(n, W, H, seed=31, radius_px=8.0)
+    cams = syn.make_batch_cameras(W, H, B)
+    params = pipeline.GaussianParams(sc, "cuda")
+    dcams = [pipeline.DeviceCamera(c, "cuda") for c in cams]
+    settings = [d.settings(3) for d in dcams]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    gm = torch.randn((B, n, 2), device="cuda", generator=g)
+    gr = torch.randn((B, n, 3), device="cuda", generator=g)
+    gc = torch.randn((B, n, 4), device="cuda", generator=g)
+    outs = [ops.preprocess_gaussians_raw(params._xyz, params._features_dc, params._features_rest, params._scaling,
+                                         params._rotation, params._opacity, rs) for rs in settings]
+    loss = sum((o[0] * gm[k]).sum() + (o[1] * gr[k]).sum() + (o[2] * gc[k]).sum() for k, o in enumerate(outs))
+    loss.backward()
+    ref = [t.grad.clone() for t in params.raw_parameters()]
+    for t in params.raw_parameters():
+        t.grad = None
+    bm2, brgb, bco, bradii, bdepths = ops.preprocess_gaussians_batched(
+        params._xyz, params._features_dc, params._features_rest, params._scaling, params._rotation, params._opacity,
+        ops.pack_cameras(settings), W, H, 3)
+    for k, o in enumerate(outs):
+        assert torch.equal(bradii[k], o[3]) and torch.equal(bdepths[k], o[4]) and torch.equal(bm2[k], o[0])
+        assert torch.equal(bco[k], o[2]) and torch.equal(brgb[k], o[1])
+        assert (o[3] > 0).sum() > 1000
+    ((bm2 * gm).sum() + (brgb * gr).sum() + (bco * gc).sum()).backward()
+    for t, r, name in zip(params.raw_parameters(), ref, ("xyz", "f_dc", "f_rest", "scaling", "rotation", "opacity")):
+        frac, _ = gu.rel_report("batched." + name, gu.npy(t.grad), gu.npy(r))
+        assert frac <= OUTLIER_FRAC, name
