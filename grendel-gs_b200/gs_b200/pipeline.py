@@ -131,6 +131,8 @@ class Trainer:
         self.history = StrategyHistory([c.uid for c in self.dcams], self.tile_y, world)
         self._strip_cache = {}
         self._cams_packed = None   # (B,40) camera table of the batched preprocess (cameras are fixed per Trainer)
+        self._strategy_cache = None
+        self._copy_stream = None
         self._loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
         self._info = {}
         self._h2d = 0
@@ -175,8 +177,32 @@ class Trainer:
         self._h2d = 0
         ops.LAST_R_TOTAL = 0
         uids = [c.uid for c in self.dcams]
-        strategies, _tasks = start_strategy(uids, self.history, self.world, self.rank)
+        ver = len(self.history.history)   # the division only changes when the cost heuristic is updated
+        if self._strategy_cache is None or self._strategy_cache[0] != ver:
+            self._strategy_cache = (ver, start_strategy(uids, self.history, self.world, self.rank)[0])
+        strategies = self._strategy_cache[1]
         settings = [c.settings(p.active_sh_degree) for c in self.dcams]
+        # "Asynchronously load ground-truth image to GPU" (loss_distribution.py:2399): the strips this rank needs are
+        # copied from pinned host memory on a side stream while preprocess / binning / blend run, and the loss waits
+        # on the copy's event.
+        gt_ready = {}
+        if not resident:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            for k, st in enumerate(strategies):
+                rows = st.local_pixel_rows(self.H)
+                if rows is None:
+                    continue
+                key = (k, rows[0], rows[1], False)
+                if key not in self._strip_cache:  # pinned, contiguous staging copy of the strip rows
+                    self._strip_cache[key] = self.gts_host[k][:, rows[0]:rows[1], :].contiguous().pin_memory()
+                h = self._strip_cache[key]
+                self._h2d += h.numel()
+                with torch.cuda.stream(self._copy_stream):
+                    d = h.to(self.device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                gt_ready[k] = (d, ev)
         if not self.fused_activations:  # the reference's five activation kernels + cat (__init__.py:902-906)
             xyz, scaling, rotation, feats, opacity = p.get_xyz, p.get_scaling, p.get_rotation, p.get_features, p.get_opacity
         collectors = [{} for _ in self.dcams]
@@ -222,7 +248,13 @@ class Trainer:
             image, *_ = ops_.render_gaussians(m2, co, rgb, depths, radii, cl, settings[k],
                                               {"stats_collector": collectors[k]})
             y0, y1 = st.local_pixel_rows(self.H)
-            l1, ss = ops_.fused_l1_ssim(image, self._gt_strip(k, y0, y1, resident), y0, y1)
+            if resident:
+                gt = self._gt_strip(k, y0, y1, True)
+            else:
+                gt, ev = gt_ready[k]
+                torch.cuda.current_stream().wait_event(ev)
+                gt.record_stream(torch.cuda.current_stream())
+            l1, ss = ops_.fused_l1_ssim(image, gt, y0, y1)
             loss = (1.0 - self.lambda_dssim) * l1 + self.lambda_dssim * (1.0 - ss)
             loss_sum = loss if loss_sum is None else loss_sum + loss
             Vp += m2.shape[0]
