@@ -36,8 +36,8 @@ extern "C" size_t gs_loss_temp_bytes(int rows, int image_width) {
 
 // temp layout: [0,16) two double accumulators; [256, ...) maps (3 maps x 3 channels x rows x W)
 __global__ void __launch_bounds__(LS_THREADS)
-k_loss_fwd(int W, int H, int row0, int rows, const float *__restrict__ image, const uint8_t *__restrict__ gt,
-           float *__restrict__ maps, double *__restrict__ sums) {
+k_loss_fwd(int W, int H, int row0, int rows, int crow0, int crow1, const float *__restrict__ image,
+           const uint8_t *__restrict__ gt, float *__restrict__ maps, double *__restrict__ sums) {
     __shared__ float s_x[LS_IN][LS_IN + 1], s_y[LS_IN][LS_IN + 1];
     __shared__ float s_h[5][LS_IN][LS_TILE + 1];
     __shared__ float s_red[2][LS_THREADS / 32];
@@ -72,6 +72,11 @@ k_loss_fwd(int W, int H, int row0, int rows, const float *__restrict__ image, co
             const int r = k / LS_TILE, c = k % LS_TILE;
             const int y = ty0 + r, x = tx0 + c;
             if (y < rows && x < W) {
+                const size_t o = (size_t)ch * SW + (size_t)y * W + x;
+                if (y < crow0 || y >= crow1) {  // halo row: feeds the neighbours' windows, carries no loss itself
+                    maps[o] = 0.f; maps[3 * SW + o] = 0.f; maps[6 * SW + o] = 0.f;
+                    continue;
+                }
                 float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
                 for (int t = 0; t < 11; t++) {
@@ -89,7 +94,6 @@ k_loss_fwd(int W, int H, int row0, int rows, const float *__restrict__ image, co
                 const float dm1 = 2.f * m2 * (B - A) * iCD - 2.f * m1 * A * B * (D - Cc) * iCD * iCD;
                 const float d11 = -A * B * iCD / D;
                 const float d12 = 2.f * A * iCD;
-                const size_t o = (size_t)ch * SW + (size_t)y * W + x;
                 maps[o] = dm1; maps[3 * SW + o] = d11; maps[6 * SW + o] = d12;
             }
         }
@@ -112,7 +116,8 @@ __global__ void k_loss_finalize(const double *__restrict__ sums, double inv_norm
 }
 
 __global__ void __launch_bounds__(LS_THREADS)
-k_loss_bwd(int W, int H, int row0, int rows, const float *__restrict__ image, const uint8_t *__restrict__ gt,
+k_loss_bwd(int W, int H, int row0, int rows, int crow0, int crow1, const float *__restrict__ image,
+           const uint8_t *__restrict__ gt,
            const float *__restrict__ maps, const float *__restrict__ grad_l1, const float *__restrict__ grad_ssim,
            float inv_norm, float *__restrict__ dimg) {
     __shared__ float s_m[3][LS_IN][LS_IN + 1];
@@ -157,7 +162,7 @@ k_loss_bwd(int W, int H, int row0, int rows, const float *__restrict__ image, co
                 const float vx = image[oi];
                 const float vy = fminf(1.f, fmaxf(0.f, (float)gt[ch * SW + (size_t)y * W + x] / 255.0f));
                 const float d = vx - vy;
-                const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+                const float sgn = (y < crow0 || y >= crow1) ? 0.f : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
                 dimg[oi] = gl1 * sgn + gss * (b0 + 2.f * vx * b1 + vy * b2);
             }
         }
@@ -165,12 +170,14 @@ k_loss_bwd(int W, int H, int row0, int rows, const float *__restrict__ image, co
     }
 }
 
-extern "C" int gs_loss_forward(int image_height, int image_width, int row0, int row1, const float *image,
-                               const uint8_t *gt_u8, float *out_l1_ssim, void *temp, size_t temp_bytes, void *stream_) {
+extern "C" int gs_loss_forward(int image_height, int image_width, int row0, int row1, int count_row0, int count_row1,
+                               const float *image, const uint8_t *gt_u8, float *out_l1_ssim, void *temp,
+                               size_t temp_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const int rows = row1 - row0;
     GS_REQUIRE(image_height > 0 && image_width > 0 && row0 >= 0 && row1 <= image_height && rows > 0, "strip rows");
     GS_REQUIRE(image && gt_u8 && out_l1_ssim && temp, "null pointer");
+    GS_REQUIRE(count_row0 >= row0 && count_row1 <= row1 && count_row1 >= count_row0, "count rows must lie inside [row0,row1)");
     if (temp_bytes < gs_loss_temp_bytes(rows, image_width)) {
         gs_set_error("gs_loss_forward: temp too small");
         return GS_ENOMEM;
@@ -182,20 +189,22 @@ extern "C" int gs_loss_forward(int image_height, int image_width, int row0, int 
     GS_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), stream));
     dim3 grid((image_width + LS_TILE - 1) / LS_TILE, (rows + LS_TILE - 1) / LS_TILE);
     GsStageTimer timer(GS_STAGE_LOSS_FWD, stream);
-    k_loss_fwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, image, gt_u8, maps, sums);
+    k_loss_fwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, count_row0 - row0, count_row1 - row0,
+                                                image, gt_u8, maps, sums);
     GS_LAUNCH_CHECK();
     k_loss_finalize<<<1, 1, 0, stream>>>(sums, 1.0 / (3.0 * (double)image_height * (double)image_width), out_l1_ssim);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
 
-extern "C" int gs_loss_backward(int image_height, int image_width, int row0, int row1, const float *image,
-                                const uint8_t *gt_u8, const void *temp, const float *grad_l1, const float *grad_ssim,
-                                float *dL_dimage, void *stream_) {
+extern "C" int gs_loss_backward(int image_height, int image_width, int row0, int row1, int count_row0, int count_row1,
+                                const float *image, const uint8_t *gt_u8, const void *temp, const float *grad_l1,
+                                const float *grad_ssim, float *dL_dimage, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const int rows = row1 - row0;
     GS_REQUIRE(image_height > 0 && image_width > 0 && row0 >= 0 && row1 <= image_height && rows > 0, "strip rows");
     GS_REQUIRE(image && gt_u8 && temp && grad_l1 && grad_ssim && dL_dimage, "null pointer");
+    GS_REQUIRE(count_row0 >= row0 && count_row1 <= row1 && count_row1 >= count_row0, "count rows must lie inside [row0,row1)");
     int rc = ensure_gauss();
     if (rc != GS_OK) return rc;
     const float *maps = (const float *)((const char *)temp + 256);
@@ -209,7 +218,8 @@ extern "C" int gs_loss_backward(int image_height, int image_width, int row0, int
     }
     dim3 grid((image_width + LS_TILE - 1) / LS_TILE, (rows + LS_TILE - 1) / LS_TILE);
     GsStageTimer timer(GS_STAGE_LOSS_BWD, stream);
-    k_loss_bwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, image, gt_u8, maps, grad_l1,
+    k_loss_bwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, count_row0 - row0, count_row1 - row0,
+                                                image, gt_u8, maps, grad_l1,
                                                 grad_ssim, (float)(1.0 / (3.0 * (double)image_height * (double)image_width)),
                                                 dL_dimage);
     GS_LAUNCH_CHECK();

@@ -346,7 +346,7 @@ class _FusedL1SSIM(torch.autograd.Function):
     """Per-strip (Ll1, ssim) of loss_distribution.py:2536-2585 in two kernels instead of ~20."""
 
     @staticmethod
-    def forward(ctx, image, gt_u8, row0, row1):
+    def forward(ctx, image, gt_u8, row0, row1, crow0, crow1):
         image = _f32c(image, "image")
         if gt_u8.dtype != torch.uint8 or not gt_u8.is_cuda:
             raise TypeError("gt strip must be a CUDA uint8 tensor (3, rows, W)")
@@ -358,9 +358,9 @@ class _FusedL1SSIM(torch.autograd.Function):
         tb = _lib.query("gs_loss_temp_bytes", rows, W)
         temp = torch.empty((tb,), dtype=torch.uint8, device=image.device)
         out = torch.empty((2,), dtype=torch.float32, device=image.device)
-        _lib.call("gs_loss_forward", H, W, row0, row1, image.data_ptr(), gt_u8.data_ptr(), out.data_ptr(),
+        _lib.call("gs_loss_forward", H, W, row0, row1, crow0, crow1, image.data_ptr(), gt_u8.data_ptr(), out.data_ptr(),
                   temp.data_ptr(), tb, _stream())
-        ctx.rows = (row0, row1)
+        ctx.rows = (row0, row1, crow0, crow1)
         ctx.save_for_backward(image, gt_u8, temp)
         return out[0], out[1]
 
@@ -368,20 +368,25 @@ class _FusedL1SSIM(torch.autograd.Function):
     def backward(ctx, g_l1, g_ssim):
         image, gt_u8, temp = ctx.saved_tensors
         _, H, W = image.shape
-        row0, row1 = ctx.rows
+        row0, row1, crow0, crow1 = ctx.rows
         dev = image.device
         g_l1 = torch.zeros((), device=dev) if g_l1 is None else g_l1
         g_ssim = torch.zeros((), device=dev) if g_ssim is None else g_ssim
         g_l1, g_ssim = g_l1.to(torch.float32).contiguous(), g_ssim.to(torch.float32).contiguous()
         d_image = torch.empty_like(image)
-        _lib.call("gs_loss_backward", H, W, row0, row1, image.data_ptr(), gt_u8.data_ptr(), temp.data_ptr(),
-                  g_l1.data_ptr(), g_ssim.data_ptr(), d_image.data_ptr(), _stream())
-        return d_image, None, None, None
+        _lib.call("gs_loss_backward", H, W, row0, row1, crow0, crow1, image.data_ptr(), gt_u8.data_ptr(),
+                  temp.data_ptr(), g_l1.data_ptr(), g_ssim.data_ptr(), d_image.data_ptr(), _stream())
+        return d_image, None, None, None, None, None
 
 
-def fused_l1_ssim(image, gt_u8, row0, row1):
-    """-> (Ll1, ssim_loss) 0-dim tensors, both normalised by 3*H*W of the FULL image."""
-    return _FusedL1SSIM.apply(image, gt_u8, int(row0), int(row1))
+def fused_l1_ssim(image, gt_u8, row0, row1, count_row0=None, count_row1=None):
+    """-> (Ll1, ssim_loss) 0-dim tensors, both normalised by 3*H*W of the FULL image.
+    Rows [row0,row1) of `image` (and the (3,row1-row0,W) uint8 `gt_u8`) form the window the 11x11 SSIM filter sees;
+    only rows [count_row0,count_row1) (default: the whole window) are summed -- pass a window widened by exchanged halo
+    rows to make strip losses add up to the full-image loss (border-pixel exchange, loss_distribution.py:601-972)."""
+    c0 = int(row0) if count_row0 is None else int(count_row0)
+    c1 = int(row1) if count_row1 is None else int(count_row1)
+    return _FusedL1SSIM.apply(image, gt_u8, int(row0), int(row1), c0, c1)
 
 
 # ---------------------------------------------------------------------------------------------------------

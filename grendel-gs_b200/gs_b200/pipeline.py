@@ -113,12 +113,13 @@ class Trainer:
     """
 
     def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None,
-                 fused_activations=True):
+                 fused_activations=True, border_exchange=False):
         from . import exchange as _ex
         self._ex = _ex
         self.device, self.rank, self.world, self.group = device, rank, world, group
         self.lambda_dssim = lambda_dssim
         self.fused_activations = fused_activations
+        self.border_exchange = border_exchange   # legacy row L1: exchange 5 halo rows so strip losses sum to the full-image loss
         n = scene["means3D"].shape[0]
         lo, hi = n * rank // world, n * (rank + 1) // world
         self.params = GaussianParams({k: v[lo:hi] for k, v in scene.items()}, device)
@@ -248,13 +249,18 @@ class Trainer:
             image, *_ = ops_.render_gaussians(m2, co, rgb, depths, radii, cl, settings[k],
                                               {"stats_collector": collectors[k]})
             y0, y1 = st.local_pixel_rows(self.H)
-            if resident:
-                gt = self._gt_strip(k, y0, y1, True)
+            if self.border_exchange and self.world > 1 and len(st.gpu_ids) > 1:
+                from . import border
+                image, (r0, r1), _ = border.add_remote_border_rows(image, st, self.H, self.group)
+                l1, ss = ops_.fused_l1_ssim(image, self.gts_dev[k][:, r0:r1, :].contiguous(), r0, r1, y0, y1)
             else:
-                gt, ev = gt_ready[k]
-                torch.cuda.current_stream().wait_event(ev)
-                gt.record_stream(torch.cuda.current_stream())
-            l1, ss = ops_.fused_l1_ssim(image, gt, y0, y1)
+                if resident:
+                    gt = self._gt_strip(k, y0, y1, True)
+                else:
+                    gt, ev = gt_ready[k]
+                    torch.cuda.current_stream().wait_event(ev)
+                    gt.record_stream(torch.cuda.current_stream())
+                l1, ss = ops_.fused_l1_ssim(image, gt, y0, y1)
             loss = (1.0 - self.lambda_dssim) * l1 + self.lambda_dssim * (1.0 - ss)
             loss_sum = loss if loss_sum is None else loss_sum + loss
             Vp += m2.shape[0]

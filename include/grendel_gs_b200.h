@@ -208,12 +208,18 @@ GS_API const char *gs_profile_stage_name(int stage);
  * out_l1_ssim: (2) float = { sum|x-y| , sum ssim_map } / (3*H*W)  -- the Ll1 and ssim_loss of :2571,2576.
  * temp (gs_loss_temp_bytes) keeps three derivative maps for the backward.
  * backward: dL_dimage (3,H,W) = grad_l1[0]*dLl1/dimage + grad_ssim[0]*dssim/dimage, with grad_* DEVICE
- * scalars (the autograd upstream gradients; no host sync); rows outside the strip are written 0. */
+ * scalars (the autograd upstream gradients; no host sync); rows outside the strip are written 0.
+ * [count_row0,count_row1) within [row0,row1) are the rows whose pixels are SUMMED; the other rows of the window only
+ * feed the 11x11 SSIM windows of their neighbours -- the live path passes count = window (zero padding at strip edges),
+ * the border-pixel exchange of loss_distribution.py:601-972 passes a window widened by the 5 halo rows received from the
+ * neighbouring strips, which makes the sum of the strip losses equal the full-image loss. */
 GS_API size_t gs_loss_temp_bytes(int rows, int image_width);
-GS_API int gs_loss_forward(int image_height, int image_width, int row0, int row1, const float *image, const uint8_t *gt_u8,
-                    float *out_l1_ssim, void *temp, size_t temp_bytes, void *stream);
-GS_API int gs_loss_backward(int image_height, int image_width, int row0, int row1, const float *image, const uint8_t *gt_u8,
-                     const void *temp, const float *grad_l1, const float *grad_ssim, float *dL_dimage, void *stream);
+GS_API int gs_loss_forward(int image_height, int image_width, int row0, int row1, int count_row0, int count_row1,
+                           const float *image, const uint8_t *gt_u8, float *out_l1_ssim, void *temp, size_t temp_bytes,
+                           void *stream);
+GS_API int gs_loss_backward(int image_height, int image_width, int row0, int row1, int count_row0, int count_row1,
+                            const float *image, const uint8_t *gt_u8, const void *temp, const float *grad_l1,
+                            const float *grad_ssim, float *dL_dimage, void *stream);
 
 /* ---- all-to-all staging -- gaussian_renderer/__init__.py:590-607,651-658 --------------------------
  * Replaces the per-(destination, camera) nonzero() + index_select + torch.cat glue around the sparse

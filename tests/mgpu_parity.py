@@ -133,6 +133,42 @@ def main():
         assert torch.allclose(pa.grad, pb.grad, rtol=1e-6, atol=1e-6), "fused sparse gradient sync != dense all-reduce"
     if rank == 0:
         print(f"[mgpu] fused sparse gradient all-reduce: {n_touched} of {P2} Gaussians touched, matches dense all-reduce")
+
+    # ---- 4. border-pixel exchange (row L1): ONE camera split over all ranks; strip losses must add up to the
+    #         FULL-image loss and the gradients must equal the single-GPU full-image gradients -----------------
+    if tr.tile_y < 3 * world:  # 13 tile rows cannot be cut into `world` strips of >= 2 rows
+        if rank == 0:
+            print(f"[mgpu] border exchange: skipped at world_size {world} (image too short for {world} strips)")
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    tr2 = pipeline.Trainer(scene, cams[:1], [torch.from_numpy(gts[0]).pin_memory()], dev, rank, world, border_exchange=True)
+    loss2 = tr2.step(resident=False)
+    l2 = [torch.zeros((), device=dev) for _ in range(world)]
+    dist.all_gather(l2, torch.tensor(loss2, device=dev))
+    g2 = {}
+    for n in names:
+        g = getattr(tr2.params, n).grad.contiguous()
+        parts = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(parts, g)
+        g2[n] = torch.cat(parts).cpu().numpy()
+    if rank == 0:
+        ref2 = o.train_step(scene, cams[0], gts[0])
+        # each strip adds lambda*(1 - its partial ssim): the constant lambda appears once per strip
+        got = float(sum(float(x) for x in l2)) - 0.2 * (world - 1)
+        print(f"[mgpu] border exchange: strip losses sum to {got:.6f}, full-image oracle loss {ref2['loss']:.6f}")
+        assert abs(got - ref2["loss"]) <= 1e-4 * abs(ref2["loss"])
+        e = ref2["grads"]
+        gq2 = e["rotations"]
+        refb = {"_xyz": e["means3D"], "_features_dc": e["shs"][:, :1], "_features_rest": e["shs"][:, 1:],
+                "_scaling": e["scales"] * scene["scales"], "_opacity": e["opacities"] * op * (1 - op),
+                "_rotation": gq2 - q * (q * gq2).sum(1, keepdims=True)}
+        for n in names:
+            a, b = g2[n].astype(np.float64), refb[n].astype(np.float64)
+            rms = np.sqrt((b ** 2).mean())
+            badf = (np.abs(a - b) > 1e-4 * np.abs(b) + 1e-4 * rms).mean()
+            assert badf <= 1e-3, ("border exchange gradient", n, badf)
+        print("[mgpu] border exchange: gradients equal the full-image (single-GPU) gradients: PASS")
     dist.barrier()
     dist.destroy_process_group()
 
