@@ -76,10 +76,10 @@ extern "C" int gs_get_local2j_ids_bool_rects(int P, int image_height, int image_
 }
 
 // ---- all-to-all staging ---------------------------------------------------------------------
-// One camera's routing mask (P, ncols) -> dense 11-float rows per destination column, splat order kept
-// (the order the reference gets from nonzero(): gaussian_renderer/__init__.py:590-607, workload_division.py:741).
 // Row = means2D(2) rgb(3) conic_opacity(4) radius-as-float depth   (gaussian_renderer/__init__.py:651-658)
 // Gradient row = d means2D(2) d rgb(3) d conic_opacity(4).
+// gs_route_scan: exclusive ranks of the flagged entries of a (P, ncols) byte mask in column-major order (also used
+// with ncols = 1 by the sparse gradient all-reduce below).
 #define GRAD_FLOATS 9
 #define MAX_COLS 16
 
@@ -129,162 +129,6 @@ extern "C" int gs_route_scan(int P, int ncols, const uint8_t *mask, int32_t *gpo
     GsStageTimer timer(GS_STAGE_PACK, stream);
     GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, gpos, P * ncols, stream));
     k_colstart<<<1, 32, 0, stream>>>(P, ncols, mask, gpos, colstart);
-    GS_LAUNCH_CHECK();
-    return GS_OK;
-}
-
-__global__ void __launch_bounds__(DT_THREADS)
-k_pack_rows(int P, int ncols, const uint8_t *__restrict__ mask, const int32_t *__restrict__ gpos,
-            const int32_t *__restrict__ colstart, Cols dst_off, const float *__restrict__ means2D,
-            const float *__restrict__ rgb, const float *__restrict__ conic_opacity, const int32_t *__restrict__ radii,
-            const float *__restrict__ depths, float *__restrict__ out) {
-    const int i = blockIdx.x * DT_THREADS + threadIdx.x;
-    if (i >= P) return;
-    bool any = false;
-    for (int c = 0; c < ncols; c++) any |= mask[(size_t)i * ncols + c] != 0;
-    if (!any) return;
-    const float2 m = *reinterpret_cast<const float2 *>(means2D + 2 * i);
-    const float4 co = *reinterpret_cast<const float4 *>(conic_opacity + 4 * i);
-    const float r0 = rgb[3 * i], r1 = rgb[3 * i + 1], r2 = rgb[3 * i + 2];
-    const float rad = (float)radii[i], dep = depths[i];
-    for (int c = 0; c < ncols; c++) {
-        if (!mask[(size_t)i * ncols + c]) continue;
-        float *o = out + (size_t)(dst_off.v[c] + gpos[(size_t)c * P + i] - colstart[c]) * ROW_FLOATS;
-        o[0] = m.x; o[1] = m.y; o[2] = r0; o[3] = r1; o[4] = r2;
-        o[5] = co.x; o[6] = co.y; o[7] = co.z; o[8] = co.w; o[9] = rad; o[10] = dep;
-    }
-}
-
-// dst_off_host: HOST array (ncols): first row of column c inside `out`.
-extern "C" int gs_pack_rows(int P, int ncols, const uint8_t *mask, const int32_t *gpos, const int32_t *colstart,
-                            const int32_t *dst_off_host, const float *means2D, const float *rgb,
-                            const float *conic_opacity, const int32_t *radii, const float *depths, float *out,
-                            void *stream) {
-    GS_REQUIRE(P >= 0 && ncols > 0 && ncols <= MAX_COLS, "sizes");
-    if (P == 0) return GS_OK;
-    GS_REQUIRE(mask && gpos && colstart && dst_off_host && means2D && rgb && conic_opacity && radii && depths && out,
-               "null pointer");
-    Cols off;
-    for (int c = 0; c < MAX_COLS; c++) off.v[c] = c < ncols ? dst_off_host[c] : 0;
-    GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
-    k_pack_rows<<<(P + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(
-        P, ncols, mask, gpos, colstart, off, means2D, rgb, conic_opacity, radii, depths, out);
-    GS_LAUNCH_CHECK();
-    return GS_OK;
-}
-
-// Received rows of one camera = up to 16 segments of the recv buffer (one per source rank), concatenated.
-struct Segs { int32_t off[MAX_COLS]; int32_t start[MAX_COLS + 1]; int n; };
-
-__device__ __forceinline__ int seg_row(const Segs &s, int r) {
-    int k = 0;
-    while (k + 1 < s.n && r >= s.start[k + 1]) k++;
-    return s.off[k] + (r - s.start[k]);
-}
-
-__global__ void __launch_bounds__(DT_THREADS)
-k_unpack_rows(int n, Segs segs, const float *__restrict__ rows, float *__restrict__ means2D, float *__restrict__ rgb,
-              float *__restrict__ conic_opacity, int32_t *__restrict__ radii, float *__restrict__ depths) {
-    const int i = blockIdx.x * DT_THREADS + threadIdx.x;
-    if (i >= n) return;
-    const float *r = rows + (size_t)seg_row(segs, i) * ROW_FLOATS;
-    means2D[2 * i] = r[0]; means2D[2 * i + 1] = r[1];
-    rgb[3 * i] = r[2]; rgb[3 * i + 1] = r[3]; rgb[3 * i + 2] = r[4];
-    *reinterpret_cast<float4 *>(conic_opacity + 4 * i) = make_float4(r[5], r[6], r[7], r[8]);
-    radii[i] = (int32_t)r[9];
-    depths[i] = r[10];
-}
-
-static int make_segs(int nseg, const int32_t *off_host, const int32_t *len_host, Segs &s) {
-    GS_REQUIRE(nseg > 0 && nseg <= MAX_COLS && off_host && len_host, "segments");
-    s.n = nseg;
-    int acc = 0;
-    for (int k = 0; k < MAX_COLS; k++) {
-        s.off[k] = k < nseg ? off_host[k] : 0;
-        s.start[k] = acc;
-        if (k < nseg) acc += len_host[k];
-    }
-    s.start[MAX_COLS] = acc;
-    return acc;
-}
-
-// seg_off_host / seg_len_host: HOST arrays (nseg): first row and row count of each segment in `rows`.
-extern "C" int gs_unpack_rows(int nseg, const int32_t *seg_off_host, const int32_t *seg_len_host, const float *rows,
-                              float *means2D, float *rgb, float *conic_opacity, int32_t *radii, float *depths,
-                              void *stream) {
-    Segs s;
-    const int n = make_segs(nseg, seg_off_host, seg_len_host, s);
-    if (n < 0) return n;
-    if (n == 0) return GS_OK;
-    GS_REQUIRE(rows && means2D && rgb && conic_opacity && radii && depths, "null pointer");
-    GsStageTimer timer(GS_STAGE_UNPACK, (cudaStream_t)stream);
-    k_unpack_rows<<<(n + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(n, s, rows, means2D, rgb,
-                                                                                             conic_opacity, radii, depths);
-    GS_LAUNCH_CHECK();
-    return GS_OK;
-}
-
-// backward of unpack: the camera's (n,2)(n,3)(n,4) gradients -> 9-float rows laid out like the recv buffer
-__global__ void __launch_bounds__(DT_THREADS)
-k_pack_grad_rows(int n, Segs segs, const float *__restrict__ d_means2D, const float *__restrict__ d_rgb,
-                 const float *__restrict__ d_conic, float *__restrict__ rows) {
-    const int i = blockIdx.x * DT_THREADS + threadIdx.x;
-    if (i >= n) return;
-    float *r = rows + (size_t)seg_row(segs, i) * GRAD_FLOATS;
-    const float4 co = *reinterpret_cast<const float4 *>(d_conic + 4 * i);
-    r[0] = d_means2D[2 * i]; r[1] = d_means2D[2 * i + 1];
-    r[2] = d_rgb[3 * i]; r[3] = d_rgb[3 * i + 1]; r[4] = d_rgb[3 * i + 2];
-    r[5] = co.x; r[6] = co.y; r[7] = co.z; r[8] = co.w;
-}
-
-extern "C" int gs_pack_grad_rows(int nseg, const int32_t *seg_off_host, const int32_t *seg_len_host,
-                                 const float *d_means2D, const float *d_rgb, const float *d_conic_opacity, float *rows,
-                                 void *stream) {
-    Segs s;
-    const int n = make_segs(nseg, seg_off_host, seg_len_host, s);
-    if (n < 0) return n;
-    if (n == 0) return GS_OK;
-    GS_REQUIRE(rows && d_means2D && d_rgb && d_conic_opacity, "null pointer");
-    GsStageTimer timer(GS_STAGE_UNPACK, (cudaStream_t)stream);
-    k_pack_grad_rows<<<(n + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(n, s, d_means2D, d_rgb,
-                                                                                                d_conic_opacity, rows);
-    GS_LAUNCH_CHECK();
-    return GS_OK;
-}
-
-// backward of pack: every local splat sums the gradient rows that came back from the columns it was sent to
-// (one thread per splat: no atomics; unflagged splats get exact zeros).
-__global__ void __launch_bounds__(DT_THREADS)
-k_scatter_grad_rows(int P, int ncols, const uint8_t *__restrict__ mask, const int32_t *__restrict__ gpos,
-                    const int32_t *__restrict__ colstart, Cols src_off, const float *__restrict__ rows,
-                    float *__restrict__ d_means2D, float *__restrict__ d_rgb, float *__restrict__ d_conic) {
-    const int i = blockIdx.x * DT_THREADS + threadIdx.x;
-    if (i >= P) return;
-    float a[GRAD_FLOATS];
-#pragma unroll
-    for (int q = 0; q < GRAD_FLOATS; q++) a[q] = 0.f;
-    for (int c = 0; c < ncols; c++) {
-        if (!mask[(size_t)i * ncols + c]) continue;
-        const float *r = rows + (size_t)(src_off.v[c] + gpos[(size_t)c * P + i] - colstart[c]) * GRAD_FLOATS;
-#pragma unroll
-        for (int q = 0; q < GRAD_FLOATS; q++) a[q] += r[q];
-    }
-    d_means2D[2 * i] = a[0]; d_means2D[2 * i + 1] = a[1];
-    d_rgb[3 * i] = a[2]; d_rgb[3 * i + 1] = a[3]; d_rgb[3 * i + 2] = a[4];
-    *reinterpret_cast<float4 *>(d_conic + 4 * i) = make_float4(a[5], a[6], a[7], a[8]);
-}
-
-extern "C" int gs_scatter_grad_rows(int P, int ncols, const uint8_t *mask, const int32_t *gpos, const int32_t *colstart,
-                                    const int32_t *src_off_host, const float *rows, float *d_means2D, float *d_rgb,
-                                    float *d_conic_opacity, void *stream) {
-    GS_REQUIRE(P >= 0 && ncols > 0 && ncols <= MAX_COLS, "sizes");
-    if (P == 0) return GS_OK;
-    GS_REQUIRE(mask && gpos && colstart && src_off_host && d_means2D && d_rgb && d_conic_opacity, "null pointer");
-    Cols off;
-    for (int c = 0; c < MAX_COLS; c++) off.v[c] = c < ncols ? src_off_host[c] : 0;
-    GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
-    k_scatter_grad_rows<<<(P + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(
-        P, ncols, mask, gpos, colstart, off, rows, d_means2D, d_rgb, d_conic_opacity);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

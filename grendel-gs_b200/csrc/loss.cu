@@ -17,16 +17,18 @@
 #define LS_THREADS 256
 
 __device__ __constant__ float c_gauss[11];
-static bool g_gauss_ready = false;
+static unsigned long long g_gauss_ready = 0ull;  // bit d: window uploaded to device d's constant memory
 
 static int ensure_gauss() {
-    if (g_gauss_ready) return GS_OK;
+    int dev = 0;
+    GS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && ((g_gauss_ready >> dev) & 1ull)) return GS_OK;
     // utils/loss_utils.py:26-34: fp32 exp values normalised in fp32
     float g[11], s = 0.f;
     for (int k = 0; k < 11; k++) { g[k] = (float)exp(-((double)(k - 5) * (k - 5)) / (2.0 * 1.5 * 1.5)); s += g[k]; }
     for (int k = 0; k < 11; k++) g[k] = g[k] / s;
     GS_CUDA_TRY(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
-    g_gauss_ready = true;
+    if (dev < 64) g_gauss_ready |= 1ull << dev;
     return GS_OK;
 }
 

@@ -46,10 +46,6 @@ SIGNATURES = {
     "gs_loss_backward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_route_scan_temp_bytes": (_sz, [_i, _i]),
     "gs_route_scan": (_i, [_i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "gs_pack_rows": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gs_unpack_rows": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gs_pack_grad_rows": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gs_scatter_grad_rows": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_xchg_temp_bytes": (_sz, [_i, _i, _i]),
     "gs_xchg_route": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gs_xchg_pack": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -3,7 +3,8 @@
 Restates /root/reference/gaussian_renderer/__init__.py:542-698 (all_to_all_communication_final):
 every rank projects its own Gaussian shard for all B cameras, then sends each projected splat to the
 ranks whose tile-row strip its rectangle touches.  Differences from the reference's Python glue:
-  * one fused scan + pack kernel per camera writes straight into the send buffer (no W x B
+  * ONE launch per stage for all B cameras: routing flags are laid out [destination][camera][splat], so a single
+    exclusive scan yields every row of the send buffer and the pack kernel writes straight into it (no W x B
     nonzero()/index_select/cat, workload_division.py:741-742, __init__.py:590-607);
   * ONE all_to_all_single of 11-float rows forward (means2D, rgb, conic_opacity, radius, depth) instead
     of two collectives, ONE of 9-float rows backward; one host sync (the counts) instead of W+2;

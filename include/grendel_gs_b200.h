@@ -223,29 +223,14 @@ GS_API int gs_loss_backward(int image_height, int image_width, int row0, int row
 
 /* ---- all-to-all staging -- gaussian_renderer/__init__.py:590-607,651-658 --------------------------
  * Replaces the per-(destination, camera) nonzero() + index_select + torch.cat glue around the sparse
- * all-to-all.  For ONE camera with routing mask (P, ncols) from gs_get_local2j_ids_bool:
- *   gs_route_scan        exclusive ranks of every flagged (column, splat) + per-column starts
- *   gs_pack_rows         dense 11-float rows (means2D 2, rgb 3, conic_opacity 4, radius as float, depth)
- *                        per destination column, splat order kept, written at HOST-given row offsets
- *   gs_unpack_rows       received segments (one per source rank) -> the camera's operator inputs
- *   gs_pack_grad_rows    backward of unpack: (n,2)(n,3)(n,4) gradients -> 9-float rows
- *   gs_scatter_grad_rows backward of pack: each local splat sums the rows of the columns it went to
- * ncols <= 16.  *_host arguments are HOST int32 arrays (passed to the kernels by value). */
+ * all-to-all: rows of 11 floats forward (means2D 2, rgb 3, conic_opacity 4, radius as float, depth), 9 floats
+ * backward.  gs_route_scan is the building block: exclusive ranks of the flagged entries of a (P, ncols) byte mask
+ * taken in column-major order (gpos, ncols*P) and the per-column starts (colstart, ncols+1); ncols <= 16. */
 GS_API size_t gs_route_scan_temp_bytes(int P, int ncols);
 GS_API int gs_route_scan(int P, int ncols, const uint8_t *mask, int32_t *gpos, int32_t *colstart, void *temp,
                          size_t temp_bytes, void *stream);
-GS_API int gs_pack_rows(int P, int ncols, const uint8_t *mask, const int32_t *gpos, const int32_t *colstart,
-                        const int32_t *dst_off_host, const float *means2D, const float *rgb, const float *conic_opacity,
-                        const int32_t *radii, const float *depths, float *out, void *stream);
-GS_API int gs_unpack_rows(int nseg, const int32_t *seg_off_host, const int32_t *seg_len_host, const float *rows,
-                          float *means2D, float *rgb, float *conic_opacity, int32_t *radii, float *depths, void *stream);
-GS_API int gs_pack_grad_rows(int nseg, const int32_t *seg_off_host, const int32_t *seg_len_host, const float *d_means2D,
-                             const float *d_rgb, const float *d_conic_opacity, float *rows, void *stream);
-GS_API int gs_scatter_grad_rows(int P, int ncols, const uint8_t *mask, const int32_t *gpos, const int32_t *colstart,
-                                const int32_t *src_off_host, const float *rows, float *d_means2D, float *d_rgb,
-                                float *d_conic_opacity, void *stream);
 
-/* Batched form: ALL B cameras of a step per launch (B, W <= 16; B*W <= 128 non-empty (source, camera) segments).
+/* Exchange of ALL B cameras of a step, one launch per stage (B, W <= 16; B*W <= 128 non-empty (source, camera) segments).
  * Flags / scan positions are laid out [destination rank j][camera k][splat i] -- the all_to_all_single send layout --
  * so gpos IS the row index in the send buffer.  *_ptrs_host are HOST arrays of B device pointers (one per camera);
  * row_lo/row_hi_host are HOST (B*W) tile-row ranges [lo,hi) of camera k owned by global rank j (row strips of

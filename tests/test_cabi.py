@@ -27,7 +27,7 @@ def test_header_declares_the_whole_hot_path():
     names = declared_symbols()
     for must in ("gs_preprocess_forward", "gs_preprocess_backward", "gs_render_count", "gs_render_forward",
                  "gs_render_backward", "gs_get_local2j_ids_bool", "gs_get_block_xy", "gs_loss_forward",
-                 "gs_loss_backward", "gs_route_scan", "gs_pack_rows", "gs_unpack_rows", "gs_pack_grad_rows", "gs_scatter_grad_rows", "gs_profile_read"):
+                 "gs_loss_backward", "gs_route_scan", "gs_xchg_route", "gs_xchg_pack", "gs_xchg_unpack", "gs_xchg_pack_grad", "gs_xchg_scatter_grad", "gs_sparse_grad_pack", "gs_preprocess_forward_batched", "gs_profile_read"):
         assert must in names
 
 
