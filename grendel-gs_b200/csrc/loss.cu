@@ -5,7 +5,8 @@
 //   ssim = sum ssim_map(x,y) / (3 H W)          (11x11 Gaussian window sigma 1.5, ZERO padding at the strip
 //                                               edges -- the live path exchanges no halo)
 // with x = rendered strip rows [row0,row1) of the full (3,H,W) image, y = clamp(gt_u8/255, 0, 1).
-// The window is applied separably (row pass then column pass) from shared memory.
+// The window is applied separably (row pass then column pass) from shared memory, four outputs per thread from a
+// 14-value sliding window in registers.
 //
 // HBM bound: forward reads 15 B and writes 36 B per pixel-channel triple (three derivative maps kept for
 // the backward), backward reads 51 B and writes 12 B; no tensor-core shaped work.
@@ -59,44 +60,64 @@ k_loss_fwd(int W, int H, int row0, int rows, int crow0, int crow1, const float *
             s_x[r][c] = vx; s_y[r][c] = vy;
         }
         __syncthreads();
-        for (int k = threadIdx.x; k < LS_IN * LS_TILE; k += LS_THREADS) {
-            const int r = k / LS_TILE, c = k % LS_TILE;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+        // row pass, 4 consecutive outputs per thread from a 14-value sliding window held in registers
+        // (28 shared loads feed 220 FMAs; one output per thread needed 22 loads for 55)
+        for (int k = threadIdx.x; k < LS_IN * (LS_TILE / 4); k += LS_THREADS) {
+            const int r = k / (LS_TILE / 4), c0 = (k % (LS_TILE / 4)) * 4;
+            float wx[14], wy[14];
 #pragma unroll
-            for (int t = 0; t < 11; t++) {
-                const float g = c_gauss[t], vx = s_x[r][c + t], vy = s_y[r][c + t];
-                a0 += g * vx; a1 += g * vy; a2 += g * vx * vx; a3 += g * vy * vy; a4 += g * vx * vy;
-            }
-            s_h[0][r][c] = a0; s_h[1][r][c] = a1; s_h[2][r][c] = a2; s_h[3][r][c] = a3; s_h[4][r][c] = a4;
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < LS_TILE * LS_TILE; k += LS_THREADS) {
-            const int r = k / LS_TILE, c = k % LS_TILE;
-            const int y = ty0 + r, x = tx0 + c;
-            if (y < rows && x < W) {
-                const size_t o = (size_t)ch * SW + (size_t)y * W + x;
-                if (y < crow0 || y >= crow1) {  // halo row: feeds the neighbours' windows, carries no loss itself
-                    maps[o] = 0.f; maps[3 * SW + o] = 0.f; maps[6 * SW + o] = 0.f;
-                    continue;
-                }
-                float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+            for (int t = 0; t < 14; t++) { wx[t] = s_x[r][c0 + t]; wy[t] = s_y[r][c0 + t]; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
 #pragma unroll
                 for (int t = 0; t < 11; t++) {
-                    const float g = c_gauss[t];
-                    m1 += g * s_h[0][r + t][c]; m2 += g * s_h[1][r + t][c]; e11 += g * s_h[2][r + t][c];
-                    e22 += g * s_h[3][r + t][c]; e12 += g * s_h[4][r + t][c];
+                    const float g = c_gauss[t], vx = wx[q + t], vy = wy[q + t];
+                    a0 += g * vx; a1 += g * vy; a2 += g * vx * vx; a3 += g * vy * vy; a4 += g * vx * vy;
                 }
-                const float s1 = e11 - m1 * m1, s2 = e22 - m2 * m2, s12 = e12 - m1 * m2;
-                const float A = 2.f * m1 * m2 + C1, B = 2.f * s12 + C2, Cc = m1 * m1 + m2 * m2 + C1, D = s1 + s2 + C2;
-                const float iCD = 1.f / (Cc * D);
-                ss += A * B * iCD;
-                const float vx = s_x[r + LS_HALO][c + LS_HALO], vy = s_y[r + LS_HALO][c + LS_HALO];
-                l1 += fabsf(vx - vy);
-                // d map / d(mu1), d(E[x^2]), d(E[xy])
-                const float dm1 = 2.f * m2 * (B - A) * iCD - 2.f * m1 * A * B * (D - Cc) * iCD * iCD;
-                const float d11 = -A * B * iCD / D;
-                const float d12 = 2.f * A * iCD;
-                maps[o] = dm1; maps[3 * SW + o] = d11; maps[6 * SW + o] = d12;
+                s_h[0][r][c0 + q] = a0; s_h[1][r][c0 + q] = a1; s_h[2][r][c0 + q] = a2; s_h[3][r][c0 + q] = a3;
+                s_h[4][r][c0 + q] = a4;
+            }
+        }
+        __syncthreads();
+        // column pass: each thread owns one column and 4 consecutive output rows (14-row window per plane)
+        {
+            const int c = threadIdx.x % LS_TILE, r0 = (threadIdx.x / LS_TILE) * 4, x = tx0 + c;
+            float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f}, e11[4] = {0.f, 0.f, 0.f, 0.f},
+                  e22[4] = {0.f, 0.f, 0.f, 0.f}, e12[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < 14; t++) {
+                const float v0 = s_h[0][r0 + t][c], v1 = s_h[1][r0 + t][c], v2 = s_h[2][r0 + t][c], v3 = s_h[3][r0 + t][c],
+                            v4 = s_h[4][r0 + t][c];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (t - q >= 0 && t - q < 11) {
+                        const float g = c_gauss[t - q];
+                        m1[q] += g * v0; m2[q] += g * v1; e11[q] += g * v2; e22[q] += g * v3; e12[q] += g * v4;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int r = r0 + q, y = ty0 + r;
+                if (y < rows && x < W) {
+                    const size_t o = (size_t)ch * SW + (size_t)y * W + x;
+                    if (y < crow0 || y >= crow1) {  // halo row: feeds the neighbours' windows, carries no loss itself
+                        maps[o] = 0.f; maps[3 * SW + o] = 0.f; maps[6 * SW + o] = 0.f;
+                    } else {
+                        const float s1 = e11[q] - m1[q] * m1[q], s2 = e22[q] - m2[q] * m2[q], s12 = e12[q] - m1[q] * m2[q];
+                        const float A = 2.f * m1[q] * m2[q] + C1, B = 2.f * s12 + C2,
+                                    Cc = m1[q] * m1[q] + m2[q] * m2[q] + C1, D = s1 + s2 + C2;
+                        const float iCD = 1.f / (Cc * D);
+                        ss += A * B * iCD;
+                        const float vx = s_x[r + LS_HALO][c + LS_HALO], vy = s_y[r + LS_HALO][c + LS_HALO];
+                        l1 += fabsf(vx - vy);
+                        // d map / d(mu1), d(E[x^2]), d(E[xy])
+                        maps[o] = 2.f * m2[q] * (B - A) * iCD - 2.f * m1[q] * A * B * (D - Cc) * iCD * iCD;
+                        maps[3 * SW + o] = -A * B * iCD / D;
+                        maps[6 * SW + o] = 2.f * A * iCD;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -139,33 +160,48 @@ k_loss_bwd(int W, int H, int row0, int rows, int crow0, int crow1, const float *
             s_m[0][r][c] = v0; s_m[1][r][c] = v1; s_m[2][r][c] = v2;
         }
         __syncthreads();
-        for (int k = threadIdx.x; k < LS_IN * LS_TILE; k += LS_THREADS) {
-            const int r = k / LS_TILE, c = k % LS_TILE;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int k = threadIdx.x; k < LS_IN * (LS_TILE / 4); k += LS_THREADS) {
+            const int r = k / (LS_TILE / 4), c0 = (k % (LS_TILE / 4)) * 4;
+            float w0[14], w1[14], w2[14];
 #pragma unroll
-            for (int t = 0; t < 11; t++) {
-                const float g = c_gauss[t];
-                a0 += g * s_m[0][r][c + t]; a1 += g * s_m[1][r][c + t]; a2 += g * s_m[2][r][c + t];
-            }
-            s_h[0][r][c] = a0; s_h[1][r][c] = a1; s_h[2][r][c] = a2;
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < LS_TILE * LS_TILE; k += LS_THREADS) {
-            const int r = k / LS_TILE, c = k % LS_TILE;
-            const int y = ty0 + r, x = tx0 + c;
-            if (y < rows && x < W) {
-                float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            for (int t = 0; t < 14; t++) { w0[t] = s_m[0][r][c0 + t]; w1[t] = s_m[1][r][c0 + t]; w2[t] = s_m[2][r][c0 + t]; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
                 for (int t = 0; t < 11; t++) {
                     const float g = c_gauss[t];
-                    b0 += g * s_h[0][r + t][c]; b1 += g * s_h[1][r + t][c]; b2 += g * s_h[2][r + t][c];
+                    a0 += g * w0[q + t]; a1 += g * w1[q + t]; a2 += g * w2[q + t];
                 }
-                const size_t oi = ch * HW + (size_t)(row0 + y) * W + x;
-                const float vx = image[oi];
-                const float vy = fminf(1.f, fmaxf(0.f, (float)gt[ch * SW + (size_t)y * W + x] / 255.0f));
-                const float d = vx - vy;
-                const float sgn = (y < crow0 || y >= crow1) ? 0.f : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
-                dimg[oi] = gl1 * sgn + gss * (b0 + 2.f * vx * b1 + vy * b2);
+                s_h[0][r][c0 + q] = a0; s_h[1][r][c0 + q] = a1; s_h[2][r][c0 + q] = a2;
+            }
+        }
+        __syncthreads();
+        {
+            const int c = threadIdx.x % LS_TILE, r0 = (threadIdx.x / LS_TILE) * 4, x = tx0 + c;
+            float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f}, b2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < 14; t++) {
+                const float v0 = s_h[0][r0 + t][c], v1 = s_h[1][r0 + t][c], v2 = s_h[2][r0 + t][c];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (t - q >= 0 && t - q < 11) {
+                        const float g = c_gauss[t - q];
+                        b0[q] += g * v0; b1[q] += g * v1; b2[q] += g * v2;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int y = ty0 + r0 + q;
+                if (y < rows && x < W) {
+                    const size_t oi = ch * HW + (size_t)(row0 + y) * W + x;
+                    const float vx = image[oi];
+                    const float vy = fminf(1.f, fmaxf(0.f, (float)gt[ch * SW + (size_t)y * W + x] / 255.0f));
+                    const float d = vx - vy;
+                    const float sgn = (y < crow0 || y >= crow1) ? 0.f : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+                    dimg[oi] = gl1 * sgn + gss * (b0[q] + 2.f * vx * b1[q] + vy * b2[q]);
+                }
             }
         }
         __syncthreads();
