@@ -111,22 +111,29 @@ def segments(layout):
     return rs, ln, cam, ds
 
 
+def _slab_ptrs(t, B):
+    """Device pointers of the B camera slices of a contiguous (B, P, ...) tensor."""
+    step = t.stride(0) * t.element_size() if B > 0 and t.dim() > 0 else 0
+    base = t.data_ptr()
+    return (C.c_void_p * B)(*[base + k * step for k in range(B)])
+
+
 class _ExchangeSplats(torch.autograd.Function):
-    """inputs: (means2D_k, rgb_k, conic_opacity_k) for k in cameras, flattened.
-    outputs: (means2D, rgb, conic_opacity) received per camera (differentiable), then (radii, depths) per camera."""
+    """inputs: means2D (B,P,2), rgb (B,P,3), conic_opacity (B,P,4) of the local shard for the B cameras.
+    outputs: (means2D, rgb, conic_opacity) received per camera (differentiable), then (radii, depths) per camera.
+    The backward returns whole (B,P,.) gradient tensors, so nothing is sliced or re-accumulated per camera."""
 
     @staticmethod
-    def forward(ctx, state, *tensors):
-        layout, aux, group = state["layout"], state["aux"], state["group"]
+    def forward(ctx, state, m2, rgb, co):
+        layout, group = state["layout"], state["group"]
         B, P, W = state["B"], state["P"], state["W"]
-        dev = tensors[0].device
+        m2, rgb, co = m2.contiguous(), rgb.contiguous(), co.contiguous()
+        radii, depths = state["radii"], state["depths"]
+        dev = m2.device
         s = ops._stream()
-        m2s = [tensors[3 * k].contiguous() for k in range(B)]
-        rgbs = [tensors[3 * k + 1].contiguous() for k in range(B)]
-        cos = [tensors[3 * k + 2].contiguous() for k in range(B)]
         send = torch.empty((max(layout.total_send, 1), ROW), dtype=torch.float32, device=dev)
-        _lib.call("gs_xchg_pack", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), _ptrs(m2s), _ptrs(rgbs),
-                  _ptrs(cos), _ptrs([a[0] for a in aux]), _ptrs([a[1] for a in aux]), send.data_ptr(), s)
+        _lib.call("gs_xchg_pack", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), _slab_ptrs(m2, B),
+                  _slab_ptrs(rgb, B), _slab_ptrs(co, B), _slab_ptrs(radii, B), _slab_ptrs(depths, B), send.data_ptr(), s)
         recv = torch.empty((max(layout.total_recv, 1), ROW), dtype=torch.float32, device=dev)
         all_to_all_single(recv[:layout.total_recv], send[:layout.total_send], layout.recv_splits, layout.send_splits, group)
         om2 = [torch.empty((n, 2), dtype=torch.float32, device=dev) for n in layout.n_recv]
@@ -162,49 +169,45 @@ class _ExchangeSplats(torch.autograd.Function):
                   _ptrs([g[3 * k + 2] for k in range(B)]), grecv.data_ptr(), s)
         gsend = torch.empty((max(layout.total_send, 1), GROW), dtype=torch.float32, device=dev)
         all_to_all_single(gsend[:layout.total_send], grecv[:layout.total_recv], layout.send_splits, layout.recv_splits, group)
-        d_m2 = [torch.empty((P, 2), dtype=torch.float32, device=dev) for _ in range(B)]
-        d_rgb = [torch.empty((P, 3), dtype=torch.float32, device=dev) for _ in range(B)]
-        d_co = [torch.empty((P, 4), dtype=torch.float32, device=dev) for _ in range(B)]
+        d_m2 = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
+        d_co = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
         _lib.call("gs_xchg_scatter_grad", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), gsend.data_ptr(),
-                  _ptrs(d_m2), _ptrs(d_rgb), _ptrs(d_co), s)
-        out = [None]
-        for k in range(B):
-            out += [d_m2[k], d_rgb[k], d_co[k]]
-        return tuple(out)
+                  _slab_ptrs(d_m2, B), _slab_ptrs(d_rgb, B), _slab_ptrs(d_co, B), s)
+        return None, d_m2, d_rgb, d_co
 
 
-def exchange(screen_params, strategies, settings, world, me, group=None):
-    """screen_params[k] = (means2D, rgb, conic_opacity, radii, depths) of the local shard for camera k.
-    Returns per camera the redistributed tuple for the strip this rank renders (empty tensors if none),
-    and the all-gathered counts cnt[i][k][j] (the reference's gpui_to_gpuj_imgk_size)."""
-    B = len(screen_params)
-    dev = screen_params[0][0].device
-    P = screen_params[0][0].shape[0]
+def exchange(means2D, rgb, conic_opacity, radii, depths, strategies, settings, world, me, group=None):
+    """means2D (B,P,2), rgb (B,P,3), conic_opacity (B,P,4), radii (B,P) int32, depths (B,P): the local shard projected
+    into the B cameras of the step (ops.preprocess_gaussians_batched, or torch.stack of per-camera results).
+    Returns per camera the redistributed tuple (means2D, rgb, conic_opacity, radii, depths) for the strip this rank
+    renders (empty tensors if none), and the all-gathered counts cnt[i][k][j] (the reference's gpui_to_gpuj_imgk_size)."""
+    B, P = means2D.shape[0], means2D.shape[1]
+    dev = means2D.device
     H, Wimg = int(settings[0].image_height), int(settings[0].image_width)
     lo, hi = [0] * (B * world), [0] * (B * world)
     for k, st in enumerate(strategies):
         for c, j in enumerate(st.gpu_ids):
             lo[k * world + j], hi[k * world + j] = st.division_pos[c], st.division_pos[c + 1]
-    aux = [(p[3].to(torch.int32).contiguous(), p[4].contiguous()) for p in screen_params]
-    m2s = [p[0].detach().contiguous() for p in screen_params]
+    radii = radii.to(torch.int32).contiguous()
+    depths = depths.contiguous()
+    m2d = means2D.detach().contiguous()
     n = max(B * P * world, 1)
     flags = torch.empty((n,), dtype=torch.uint8, device=dev)
     gpos = torch.empty((n,), dtype=torch.int32, device=dev)
     counts = torch.empty((world, B), dtype=torch.int32, device=dev)   # [dest j][camera k]
     tb = _lib.query("gs_xchg_temp_bytes", B, P, world)
     temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
-    _lib.call("gs_xchg_route", B, P, world, H, Wimg, _ptrs(m2s), _ptrs([a[0] for a in aux]), _i32(lo), _i32(hi),
+    _lib.call("gs_xchg_route", B, P, world, H, Wimg, _slab_ptrs(m2d, B), _slab_ptrs(radii, B), _i32(lo), _i32(hi),
               flags.data_ptr(), gpos.data_ptr(), counts.data_ptr(), temp.data_ptr(), tb, ops._stream())
     cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]
     layout = Layout(cnt, me, [st.gpu_ids for st in strategies])
-    state = dict(layout=layout, group=group, aux=aux, flags=flags, gpos=gpos, B=B, P=P, W=world, segs=segments(layout))
-    flat = []
-    for p in screen_params:
-        flat += [p[0], p[1], p[2]]
-    res = _ExchangeSplats.apply(state, *flat)
+    state = dict(layout=layout, group=group, radii=radii, depths=depths, flags=flags, gpos=gpos, B=B, P=P, W=world,
+                 segs=segments(layout))
+    res = _ExchangeSplats.apply(state, means2D, rgb, conic_opacity)
     out = []
     for k in range(B):
-        m2, rgb, co = res[3 * k:3 * k + 3]
-        radii, depths = res[3 * B + 2 * k:3 * B + 2 * k + 2]
-        out.append((m2, rgb, co, radii, depths))
+        m2, c3, co = res[3 * k:3 * k + 3]
+        rad, dep = res[3 * B + 2 * k:3 * B + 2 * k + 2]
+        out.append((m2, c3, co, rad, dep))
     return out, cnt

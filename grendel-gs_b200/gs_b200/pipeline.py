@@ -133,6 +133,7 @@ class Trainer:
         self._strip_cache = {}
         self._cams_packed = None   # (B,40) camera table of the batched preprocess (cameras are fixed per Trainer)
         self._strategy_cache = None
+        self._mask_cache = {}
         self._copy_stream = None
         self._loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
         self._info = {}
@@ -215,12 +216,14 @@ class Trainer:
             bm2, brgb, bco, bradii, bdepths = ops_.preprocess_gaussians_batched(
                 p._xyz, p._features_dc, p._features_rest, p._scaling, p._rotation, p._opacity, self._cams_packed,
                 self.W, self.H, p.active_sh_degree)
-            for k in range(len(settings)):
-                m2 = bm2[k]
-                m2.retain_grad()
-                screen.append((m2, brgb[k], bco[k], bradii[k], bdepths[k]))
+            bm2.retain_grad()   # (B,P,2): densification reads bm2.grad[k] (means2D.grad of camera k, densification.py:24)
+            batched = (bm2, brgb, bco, bradii, bdepths)
+            if self.world == 1:
+                for k in range(len(settings)):
+                    screen.append((bm2[k], brgb[k], bco[k], bradii[k], bdepths[k]))
             settings_loop = []
         else:
+            batched = None
             settings_loop = settings
         for k, rs in enumerate(settings_loop):
             if self.fused_activations:
@@ -231,12 +234,15 @@ class Trainer:
                                                 {"stats_collector": collectors[k]})
             out[0].retain_grad()
             screen.append(out)
-        self.means2D = [s[0] for s in screen]
+        self.means2D = batched[0] if batched is not None else [s[0] for s in screen]
         self._mark("preprocess")
         if self.world > 1:
-            redistributed, cnt = self._ex.exchange(screen, strategies, settings, self.world, self.rank, self.group)
+            if batched is None:   # per-camera results (B == 1 or unfused activations): stack into (B,P,.)
+                batched = tuple(torch.stack([s[q] for s in screen]) for q in range(5))
+            redistributed, cnt = self._ex.exchange(*batched, strategies, settings, self.world, self.rank, self.group)
         else:
             redistributed = screen
+        self._radii_local = batched[3] if batched is not None else torch.stack([s[3] for s in screen])
         self._mark("exchange")
         loss_sum = None
         Vp = Pl = 0
@@ -245,7 +251,10 @@ class Trainer:
             if rows is None:
                 continue
             m2, rgb, co, radii, depths = redistributed[k]
-            cl = st.get_compute_locally(self.tile_x, self.device)
+            ck = (tuple(st.gpu_ids), tuple(st.division_pos), st.rank)
+            if ck not in self._mask_cache:
+                self._mask_cache[ck] = st.get_compute_locally(self.tile_x, self.device)
+            cl = self._mask_cache[ck]
             image, *_ = ops_.render_gaussians(m2, co, rgb, depths, radii, cl, settings[k],
                                               {"stats_collector": collectors[k]})
             y0, y1 = st.local_pixel_rows(self.H)
@@ -269,7 +278,7 @@ class Trainer:
         loss_sum.backward()
         self._mark("backward")
         self._collectors, self._strategies = collectors, strategies
-        self._counts = dict(Vp=Vp, P_local=Pl, screen=screen)
+        self._counts = dict(Vp=Vp, P_local=Pl)
         if resident:
             return None
         self._loss_host.copy_(loss_sum.detach().reshape(1), non_blocking=True)
@@ -278,7 +287,7 @@ class Trainer:
 
     def last_info(self):
         """Realised sizes of the last step on this rank: V visible, V' splats rendered, R instances."""
-        V = sum(int((s[3] > 0).sum()) for s in self._counts["screen"])
+        V = int((self._radii_local > 0).sum())
         R = ops.LAST_R_TOTAL
         return dict(V=V, Vp=self._counts["Vp"], P_local=self._counts["P_local"], R=R)
 

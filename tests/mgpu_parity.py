@@ -46,7 +46,8 @@ def main():
         settings = [c.settings(3) for c in tr.dcams]
         screen = [ops.preprocess_gaussians_raw(p._xyz, p._features_dc, p._features_rest, p._scaling, p._rotation,
                                                p._opacity, rs) for rs in settings]
-        red, _ = tr._ex.exchange(screen, strategies, settings, world, rank)
+        stacked = tuple(torch.stack([s_[q] for s_ in screen]) for q in range(5))
+        red, _ = tr._ex.exchange(*stacked, strategies, settings, world, rank)
         for k, st in enumerate(strategies):
             img = torch.zeros((3, H, W), device=dev)
             if st.local_rows() is not None:
