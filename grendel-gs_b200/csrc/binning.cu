@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(BIN_THREADS)
 k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const float *__restrict__ conic_opacity,
               const float *__restrict__ rgb, const float *__restrict__ depths, const int32_t *__restrict__ radii,
               const uint8_t *__restrict__ compute_locally, uint32_t *__restrict__ touched,
-              uint32_t *__restrict__ depth_key, uint32_t *__restrict__ index, float *__restrict__ rec) {
+              uint32_t *__restrict__ depth_key, uint32_t *__restrict__ index, float *__restrict__ rec, int no_cull) {
     const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
     if (i >= P) return;
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
@@ -54,12 +54,17 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
         const float4 co = *reinterpret_cast<const float4 *>(conic_opacity + 4 * i);
         const float thr = -logf(255.0f * fmaxf(co.w, 1e-30f)) - GS_THR_MARGIN;
         // {d : A dx^2 + 2B dx dy + C dy^2 <= -2 thr} has half extents sqrt(t C/det), sqrt(t A/det)
-        const float t = -2.f * thr, det = co.x * co.z - co.y * co.y;
+        // det = AC - B^2 cancels catastrophically for needle-like splats (relative error ~ulp * lambda_max/lambda_min),
+        // which would shrink the box and drop real contributions: evaluate it with Kahan's FMA-compensated ab - cd,
+        // exact to ~1.5 ulp, and widen the box by 2 % on top of the half-pixel slack.
+        const float t = -2.f * thr;
+        const float bb = co.y * co.y, bb_err = __fmaf_rn(co.y, co.y, -bb);
+        const float det = __fmaf_rn(co.x, co.z, -bb) - bb_err;
         float ex = -1.f, ey = -1.f;  // never contributes
         if (t > 0.f) {
-            if (det > 0.f && co.x > 0.f && co.z > 0.f) {
-                ex = sqrtf(t * co.z / det) * 1.001f + 0.5f;
-                ey = sqrtf(t * co.x / det) * 1.001f + 0.5f;
+            if (!no_cull && det > 0.f && co.x > 0.f && co.z > 0.f) {
+                ex = sqrtf(t * co.z / det) * 1.02f + 0.5f;
+                ey = sqrtf(t * co.x / det) * 1.02f + 0.5f;
             } else {
                 ex = ey = 3.0e38f;  // degenerate conic: never cull
             }
@@ -157,7 +162,8 @@ extern "C" int gs_render_count(int P, int image_height, int image_width, const f
     {
         GsStageTimer timer(GS_STAGE_COUNT_TILES, stream);
         k_count_tiles<<<grid, BIN_THREADS, 0, stream>>>(P, image_width, image_height, means2D, conic_opacity, rgb, depths,
-                                                        radii, compute_locally, touched, dkey, index, rec);
+                                                        radii, compute_locally, touched, dkey, index, rec,
+                                                        (g_gs_debug_flags & GS_DEBUG_NO_BLOCK_CULL) ? 1 : 0);
         GS_LAUNCH_CHECK();
     }
     {

@@ -29,6 +29,12 @@ extern "C" int gs_get_block_xy(int *block_x, int *block_y, int *one_dim_block_si
 // ---- per-stage device timing -------------------------------------------------------------------
 #include <vector>
 bool g_gs_profile_on = false;
+int g_gs_debug_flags = 0;
+extern "C" int gs_debug_set(int flags) {
+    const int old = g_gs_debug_flags;
+    g_gs_debug_flags = flags;
+    return old;
+}
 namespace {
 struct StageRec {
     std::vector<cudaEvent_t> begin, end;  // event pool, reused across reads

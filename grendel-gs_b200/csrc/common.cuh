@@ -30,6 +30,7 @@ void gs_set_error(const char *fmt, ...);
 
 // ---- per-stage device timing (capi.cu) -------------------------------------------------------------
 extern bool g_gs_profile_on;
+extern int g_gs_debug_flags;  // gs_debug_set: GS_DEBUG_* bits, test-only switches
 void gs_prof_mark(int stage, bool begin, cudaStream_t stream);
 struct GsStageTimer {  // RAII: events around the launches of one stage when profiling is enabled
     int stage; cudaStream_t stream;

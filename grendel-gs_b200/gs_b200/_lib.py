@@ -41,6 +41,7 @@ SIGNATURES = {
     "gs_profile_enable": (_i, [_i]),
     "gs_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "gs_profile_stage_name": (C.c_char_p, [_i]),
+    "gs_debug_set": (_i, [_i]),
     "gs_loss_temp_bytes": (_sz, [_i, _i]),
     "gs_loss_forward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gs_loss_backward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -105,6 +106,12 @@ def ptr(t):
 
 
 STAGE_NUM = 14
+DEBUG_NO_BLOCK_CULL = 1
+
+
+def debug_set(flags):
+    """Test-only switches (include/grendel_gs_b200.h, gs_debug_set); returns the previous flags."""
+    return query("gs_debug_set", int(flags))
 
 
 def profile_enable(on=True):

@@ -202,6 +202,15 @@ GS_API int gs_profile_enable(int on);
 GS_API int gs_profile_read(int stage, double *total_ms, int64_t *launches);
 GS_API const char *gs_profile_stage_name(int stage);
 
+/* ---- test-only switches (no reference counterpart) ------------------------------------------------
+ * The blend kernels skip 4x4 / 8x4 pixel blocks a splat cannot reach with alpha >= 1/255, using per-splat
+ * extents computed in gs_render_count.  That cull must be CONSERVATIVE: it may never drop a contribution the
+ * reference (which tests alpha per pixel, cuda_rasterizer/forward.cu:513-519) would have blended.
+ * GS_DEBUG_NO_BLOCK_CULL makes gs_render_count write infinite extents, so tests can check that the culled and
+ * unculled kernels produce the same image and n_contrib.  Returns the previous flags. */
+enum { GS_DEBUG_NO_BLOCK_CULL = 1 };
+GS_API int gs_debug_set(int flags);
+
 /* ---- per-strip loss -- gaussian_renderer/loss_distribution.py:2536-2585 + utils/loss_utils.py:88-132 ----
  * image: (3,H,W) full-size render of which rows [row0,row1) are this rank's strip;
  * gt_u8: (3,row1-row0,W) uint8 ground-truth strip (camera.original_image of loss_distribution.py:2561).
