@@ -257,6 +257,21 @@ def run_ours(args):
     ms_e2e = float(t.item()) / steps
     h2d, d2h = trainer.io_bytes_per_step()
 
+    # ---- diagnostics, OUTSIDE both timed regions: wall clock per phase with a device synchronise after each phase
+    # (serialises host and device, so the phases add up to more than ms_per_step; max over ranks) ----------------
+    phase_ms = None
+    if world > 1:
+        os.environ["GS_B200_TRACE"] = "1"
+        trainer.trace = {}
+        n_tr = 5
+        for _ in range(n_tr):
+            trainer.step(resident=True)
+        del os.environ["GS_B200_TRACE"]
+        keys = sorted(trainer.trace)
+        tt = torch.tensor([trainer.trace[k] / n_tr for k in keys], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        phase_ms = {k: round(float(v), 4) for k, v in zip(keys, tt.tolist())}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,6 +333,8 @@ def run_ours(args):
             "library_calls": {"cub::DeviceScan": int(launches.get("30 InclusiveSum", 0)),
                               "cub::DeviceRadixSort": int(launches.get("50 SortPairs", 0))},
             "roofline": roofline, "clocks": clocks}
+    if phase_ms is not None:  # multi-GPU only; measured outside the timed regions (see above)
+        line["phase_ms_serialised"] = phase_ms
     if not args.no_cpu_baseline:
         r = cpu_arm(cfg, args.cpu_sample, 1, 1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

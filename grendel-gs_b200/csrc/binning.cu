@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(BIN_THREADS)
 k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const float *__restrict__ conic_opacity,
               const float *__restrict__ rgb, const float *__restrict__ depths, const int32_t *__restrict__ radii,
               const uint8_t *__restrict__ compute_locally, uint32_t *__restrict__ touched,
-              uint32_t *__restrict__ depth_key, uint32_t *__restrict__ index, float *__restrict__ rec, int no_cull) {
+              uint32_t *__restrict__ depth_key, uint32_t *__restrict__ index, float *__restrict__ rec, int no_cull,
+              const GsViews views) {
     const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
     if (i >= P) return;
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
@@ -41,8 +42,9 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
     if (r > 0) {
         int x0, y0, x1, y1;
         gs_get_rect(m.x, m.y, r, gx, gy, x0, y0, x1, y1);
+        const uint8_t *mask = compute_locally + (size_t)gs_view_of(views, i) * views.T;
         for (int y = y0; y < y1; y++) {
-            const uint8_t *row = compute_locally + y * gx;
+            const uint8_t *row = mask + y * gx;
             for (int x = x0; x < x1; x++) n += row[x] ? 1u : 0u;
         }
     }
@@ -89,7 +91,8 @@ k_gather_touched(int P, const uint32_t *__restrict__ order, const uint32_t *__re
 __global__ void __launch_bounds__(BIN_THREADS)
 k_duplicate(int P, int W, int H, const float *__restrict__ means2D, const int32_t *__restrict__ radii,
             const uint8_t *__restrict__ compute_locally, const uint32_t *__restrict__ order,
-            const uint32_t *__restrict__ offsets, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ ids) {
+            const uint32_t *__restrict__ offsets, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ ids,
+            const GsViews views) {
     const int s = blockIdx.x * BIN_THREADS + threadIdx.x;
     if (s >= P) return;
     uint32_t off = (s == 0) ? 0u : offsets[s - 1];
@@ -99,9 +102,10 @@ k_duplicate(int P, int W, int H, const float *__restrict__ means2D, const int32_
     const float2 m = *reinterpret_cast<const float2 *>(means2D + 2 * (size_t)i);
     int x0, y0, x1, y1;
     gs_get_rect(m.x, m.y, radii[i], gx, gy, x0, y0, x1, y1);
+    const int t0 = gs_view_of(views, (int)i) * views.T;  // first tile of this splat's view
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) {
-            const int t = y * gx + x;
+            const int t = t0 + y * gx + x;
             if (!compute_locally[t]) continue;
             tile_keys[off] = (uint32_t)t;
             ids[off] = i;
@@ -135,14 +139,34 @@ extern "C" size_t gs_render_count_temp_bytes(int P) {
     return 5 * align_up((size_t)(P > 0 ? P : 1) * sizeof(uint32_t), 256) + count_cub_bytes(P) + 256;
 }
 
-extern "C" int gs_render_count(int P, int image_height, int image_width, const float *means2D,
-                               const float *conic_opacity, const float *rgb, const float *depths, const int32_t *radii,
-                               const uint8_t *compute_locally, uint32_t *order, uint32_t *offsets, float *rec,
-                               void *temp, size_t temp_bytes, int64_t *R_host, void *stream_) {
+// host copy of the view table; validates it (monotone, within GS_MAX_VIEWS)
+static int make_views(int num_views, const int32_t *view_start, int T, GsViews &v) {
+    GS_REQUIRE(num_views >= 1 && num_views <= GS_MAX_VIEWS, "num_views must be in [1, GS_MAX_VIEWS]");
+    GS_REQUIRE(view_start != nullptr && view_start[0] == 0, "view_start[0] must be 0");
+    GS_REQUIRE((long long)T * num_views < (1ll << 31), "too many tiles");
+    v.n = num_views;
+    v.T = T;
+    for (int k = 0; k <= GS_MAX_VIEWS; k++) v.start[k] = view_start[k <= num_views ? k : num_views];
+    for (int k = 0; k < num_views; k++) GS_REQUIRE(v.start[k] <= v.start[k + 1], "view_start must be non-decreasing");
+    return GS_OK;
+}
+
+extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start, int image_height, int image_width,
+                                       const float *means2D, const float *conic_opacity, const float *rgb,
+                                       const float *depths, const int32_t *radii, const uint8_t *compute_locally,
+                                       uint32_t *order, uint32_t *offsets, float *rec, void *temp, size_t temp_bytes,
+                                       int64_t *R_host, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    GS_REQUIRE(P >= 0 && image_height > 0 && image_width > 0, "sizes");
+    GS_REQUIRE(image_height > 0 && image_width > 0, "sizes");
     GS_REQUIRE(R_host != nullptr, "R_host");
     *R_host = 0;
+    GsViews views;
+    {
+        const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
+        const int rc = make_views(num_views, view_start, gx * gy, views);
+        if (rc != GS_OK) return rc;
+    }
+    const int P = views.start[num_views];
     if (P == 0) return GS_OK;
     GS_REQUIRE(means2D && conic_opacity && rgb && depths && radii && compute_locally && order && offsets && rec && temp,
                "null pointer");
@@ -163,7 +187,7 @@ extern "C" int gs_render_count(int P, int image_height, int image_width, const f
         GsStageTimer timer(GS_STAGE_COUNT_TILES, stream);
         k_count_tiles<<<grid, BIN_THREADS, 0, stream>>>(P, image_width, image_height, means2D, conic_opacity, rgb, depths,
                                                         radii, compute_locally, touched, dkey, index, rec,
-                                                        (g_gs_debug_flags & GS_DEBUG_NO_BLOCK_CULL) ? 1 : 0);
+                                                        (g_gs_debug_flags & GS_DEBUG_NO_BLOCK_CULL) ? 1 : 0, views);
         GS_LAUNCH_CHECK();
     }
     {
@@ -183,6 +207,16 @@ extern "C" int gs_render_count(int P, int image_height, int image_width, const f
     return GS_OK;
 }
 
+extern "C" int gs_render_count(int P, int image_height, int image_width, const float *means2D,
+                               const float *conic_opacity, const float *rgb, const float *depths, const int32_t *radii,
+                               const uint8_t *compute_locally, uint32_t *order, uint32_t *offsets, float *rec,
+                               void *temp, size_t temp_bytes, int64_t *R_host, void *stream) {
+    GS_REQUIRE(P >= 0, "sizes");
+    const int32_t one_view[2] = {0, P};
+    return gs_render_count_batched(1, one_view, image_height, image_width, means2D, conic_opacity, rgb, depths, radii,
+                                   compute_locally, order, offsets, rec, temp, temp_bytes, R_host, stream);
+}
+
 static int tile_bits(int T) {
     int b = 0;
     while ((1ll << b) < (long long)T) b++;
@@ -197,22 +231,29 @@ extern "C" size_t gs_render_sort_temp_bytes(int64_t R) {
 }
 
 // Implemented in blend.cu
-int gs_launch_blend_forward(int64_t R, int H, int W, const float *rec, const float *bg, const uint8_t *compute_locally,
-                            const uint32_t *ranges, const uint32_t *ids_sorted, float *image, float *final_T,
-                            uint32_t *n_contrib, int64_t *stats, cudaStream_t stream);
+int gs_launch_blend_forward(int num_views, int64_t R, int H, int W, const float *rec, const float *bg,
+                            const uint8_t *compute_locally, const uint32_t *ranges, const uint32_t *ids_sorted,
+                            float *image, float *final_T, uint32_t *n_contrib, int64_t *stats, cudaStream_t stream);
 
-extern "C" int gs_render_forward(int P, int64_t R, int image_height, int image_width, const float *means2D,
-                                 const int32_t *radii, const uint8_t *compute_locally, const uint32_t *order,
-                                 const uint32_t *offsets, const float *rec, const float *bg, uint32_t *tiles_unsorted,
-                                 uint32_t *ids_unsorted, uint32_t *tiles_sorted, uint32_t *ids_sorted, void *sort_temp,
-                                 size_t sort_temp_bytes, uint32_t *ranges, float *image, float *final_T,
-                                 uint32_t *n_contrib, int64_t *stats, void *stream_) {
+extern "C" int gs_render_forward_batched(int num_views, const int32_t *view_start, int64_t R, int image_height,
+                                         int image_width, const float *means2D, const int32_t *radii,
+                                         const uint8_t *compute_locally, const uint32_t *order, const uint32_t *offsets,
+                                         const float *rec, const float *bg, uint32_t *tiles_unsorted,
+                                         uint32_t *ids_unsorted, uint32_t *tiles_sorted, uint32_t *ids_sorted,
+                                         void *sort_temp, size_t sort_temp_bytes, uint32_t *ranges, float *image,
+                                         float *final_T, uint32_t *n_contrib, int64_t *stats, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    GS_REQUIRE(P >= 0 && R >= 0 && image_height > 0 && image_width > 0, "sizes");
+    GS_REQUIRE(R >= 0 && image_height > 0 && image_width > 0, "sizes");
     GS_REQUIRE(R < (1ll << 31), "more than 2^31 splat-tile instances");
     GS_REQUIRE(compute_locally && bg && ranges && image && final_T && n_contrib, "null pointer");
     const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
-    const int T = gx * gy;
+    GsViews views;
+    {
+        const int rc = make_views(num_views, view_start, gx * gy, views);
+        if (rc != GS_OK) return rc;
+    }
+    const int P = views.start[num_views];
+    const int T = gx * gy * num_views;  // tiles of all views
     GS_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * (size_t)T, stream));
     if (R > 0) {
         GS_REQUIRE(means2D && radii && order && offsets && rec && tiles_unsorted && ids_unsorted && tiles_sorted &&
@@ -225,7 +266,8 @@ extern "C" int gs_render_forward(int P, int64_t R, int image_height, int image_w
         {
             GsStageTimer timer(GS_STAGE_DUPLICATE, stream);
             k_duplicate<<<(P + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, stream>>>(
-                P, image_width, image_height, means2D, radii, compute_locally, order, offsets, tiles_unsorted, ids_unsorted);
+                P, image_width, image_height, means2D, radii, compute_locally, order, offsets, tiles_unsorted, ids_unsorted,
+                views);
             GS_LAUNCH_CHECK();
         }
         {
@@ -239,6 +281,19 @@ extern "C" int gs_render_forward(int P, int64_t R, int image_height, int image_w
             GS_LAUNCH_CHECK();
         }
     }
-    return gs_launch_blend_forward(R, image_height, image_width, rec, bg, compute_locally, ranges, ids_sorted, image,
-                                   final_T, n_contrib, stats, stream);
+    return gs_launch_blend_forward(num_views, R, image_height, image_width, rec, bg, compute_locally, ranges, ids_sorted,
+                                   image, final_T, n_contrib, stats, stream);
+}
+
+extern "C" int gs_render_forward(int P, int64_t R, int image_height, int image_width, const float *means2D,
+                                 const int32_t *radii, const uint8_t *compute_locally, const uint32_t *order,
+                                 const uint32_t *offsets, const float *rec, const float *bg, uint32_t *tiles_unsorted,
+                                 uint32_t *ids_unsorted, uint32_t *tiles_sorted, uint32_t *ids_sorted, void *sort_temp,
+                                 size_t sort_temp_bytes, uint32_t *ranges, float *image, float *final_T,
+                                 uint32_t *n_contrib, int64_t *stats, void *stream) {
+    GS_REQUIRE(P >= 0, "sizes");
+    const int32_t one_view[2] = {0, P};
+    return gs_render_forward_batched(1, one_view, R, image_height, image_width, means2D, radii, compute_locally, order,
+                                     offsets, rec, bg, tiles_unsorted, ids_unsorted, tiles_sorted, ids_sorted, sort_temp,
+                                     sort_temp_bytes, ranges, image, final_T, n_contrib, stats, stream);
 }

@@ -78,7 +78,7 @@ struct __align__(16) SRec { float4 a; float4 b; float4 c; };
 
 template <bool STATS>
 __global__ void __launch_bounds__(BL_THREADS)
-k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restrict__ bg,
+k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
             const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
             const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
             uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats) {
@@ -86,18 +86,22 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
     __shared__ uint16_t s_cull[FW_CHUNK];
     __shared__ unsigned long long s_stats[3];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
-    const int tile = blockIdx.x;
+    // blockIdx.x = view * tiles_per_view + tile: the views' tile arrays and images are concatenated (GsViews)
+    const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
     const int lane = threadIdx.x & 31;
     const Where me = where_am_i(tile, gx);
     const int px = me.px, py = me.py;
     const bool inside = px < W && py < H;
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
-    if (!compute_locally[tile]) {  // non-local tiles must read exactly 0 (loss_distribution.py:1875)
+    image += (size_t)view * 3 * HW;
+    final_T += (size_t)view * HW;
+    n_contrib += (size_t)view * HW;
+    if (!compute_locally[blockIdx.x]) {  // non-local tiles must read exactly 0 (loss_distribution.py:1875)
         if (inside) { image[pix] = 0.f; image[HW + pix] = 0.f; image[2 * HW + pix] = 0.f; }
         return;
     }
-    const uint2 range = ranges[tile];
+    const uint2 range = ranges[blockIdx.x];
     const int total = (int)(range.y - range.x);
     const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
     const float qnan = __int_as_float(0x7fc00000);
@@ -175,7 +179,7 @@ k_blend_fwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
         }
         if (lane == 0) { atomicAdd(&s_stats[0], v0); atomicAdd(&s_stats[1], v1); atomicAdd(&s_stats[2], v2); }
         __syncthreads();
-        if (threadIdx.x < 3) atomicAdd(&stats[threadIdx.x], s_stats[threadIdx.x]);
+        if (threadIdx.x < 3) atomicAdd(&stats[3 * view + threadIdx.x], s_stats[threadIdx.x]);
     }
 }
 
@@ -236,7 +240,7 @@ GS_D void warp_reduce9(float v[9], int lane) {
 }
 
 __global__ void __launch_bounds__(BL_THREADS)
-k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restrict__ bg,
+k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
             const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
             const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
             const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
@@ -248,15 +252,18 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
     __shared__ uint32_t s_mask[BL_WARPS][BW8_CHUNK / 32];
     __shared__ uint32_t s_max[BL_WARPS];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
-    const int tile = blockIdx.x;
-    if (!compute_locally[tile]) return;
+    if (!compute_locally[blockIdx.x]) return;
+    const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int px, py;
     pixel_of_thread(tile, gx, px, py);
     const bool inside = px < W && py < H;
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
-    const uint2 range = ranges[tile];
+    final_T += (size_t)view * HW;
+    n_contrib += (size_t)view * HW;
+    dL_dimage += (size_t)view * 3 * HW;
+    const uint2 range = ranges[blockIdx.x];
     const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
     const float pxf = (float)px, pyf = (float)py;
     const float T_final = inside ? final_T[pix] : 0.f;
@@ -377,22 +384,23 @@ k_blend_bwd(int W, int H, const float4 *__restrict__ rec, const float *__restric
     }
 }
 
-int gs_launch_blend_forward(int64_t R, int H, int W, const float *rec, const float *bg, const uint8_t *compute_locally,
-                            const uint32_t *ranges, const uint32_t *ids_sorted, float *image, float *final_T,
-                            uint32_t *n_contrib, int64_t *stats, cudaStream_t stream) {
+int gs_launch_blend_forward(int num_views, int64_t R, int H, int W, const float *rec, const float *bg,
+                            const uint8_t *compute_locally, const uint32_t *ranges, const uint32_t *ids_sorted,
+                            float *image, float *final_T, uint32_t *n_contrib, int64_t *stats, cudaStream_t stream) {
     (void)R;
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
-    if (stats) GS_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t), stream));
+    const int T1 = gx * gy;
+    if (stats) GS_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t) * (size_t)num_views, stream));
     GsStageTimer timer(GS_STAGE_BLEND_FWD, stream);
     auto *st = reinterpret_cast<unsigned long long *>(stats);
     if (stats)
-        k_blend_fwd<true><<<gx * gy, BL_THREADS, 0, stream>>>(W, H, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
-                                                              reinterpret_cast<const uint2 *>(ranges), ids_sorted, image,
-                                                              final_T, n_contrib, st);
+        k_blend_fwd<true><<<T1 * num_views, BL_THREADS, 0, stream>>>(
+            W, H, T1, reinterpret_cast<const float4 *>(rec), bg, compute_locally, reinterpret_cast<const uint2 *>(ranges),
+            ids_sorted, image, final_T, n_contrib, st);
     else
-        k_blend_fwd<false><<<gx * gy, BL_THREADS, 0, stream>>>(W, H, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
-                                                               reinterpret_cast<const uint2 *>(ranges), ids_sorted, image,
-                                                               final_T, n_contrib, st);
+        k_blend_fwd<false><<<T1 * num_views, BL_THREADS, 0, stream>>>(
+            W, H, T1, reinterpret_cast<const float4 *>(rec), bg, compute_locally, reinterpret_cast<const uint2 *>(ranges),
+            ids_sorted, image, final_T, n_contrib, st);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
@@ -401,8 +409,18 @@ extern "C" int gs_render_backward(int P, int64_t R, int image_height, int image_
                                   const float *bg, const uint8_t *compute_locally, const uint32_t *ranges,
                                   const uint32_t *ids_sorted, const float *final_T, const uint32_t *n_contrib,
                                   const float *dL_dimage, float *dL_dmeans2D, float *dL_dconic_opacity, float *dL_drgb,
-                                  void *stream_) {
+                                  void *stream) {
+    return gs_render_backward_batched(1, P, R, image_height, image_width, rec, bg, compute_locally, ranges, ids_sorted,
+                                      final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity, dL_drgb, stream);
+}
+
+extern "C" int gs_render_backward_batched(int num_views, int P, int64_t R, int image_height, int image_width,
+                                          const float *rec, const float *bg, const uint8_t *compute_locally,
+                                          const uint32_t *ranges, const uint32_t *ids_sorted, const float *final_T,
+                                          const uint32_t *n_contrib, const float *dL_dimage, float *dL_dmeans2D,
+                                          float *dL_dconic_opacity, float *dL_drgb, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    GS_REQUIRE(num_views >= 1 && num_views <= GS_MAX_VIEWS, "num_views must be in [1, GS_MAX_VIEWS]");
     GS_REQUIRE(P >= 0 && R >= 0 && image_height > 0 && image_width > 0, "sizes");
     if (P == 0) return GS_OK;
     GS_REQUIRE(dL_dmeans2D && dL_dconic_opacity && dL_drgb, "null output");
@@ -413,10 +431,10 @@ extern "C" int gs_render_backward(int P, int64_t R, int image_height, int image_
     GS_REQUIRE(rec && bg && compute_locally && ranges && ids_sorted && final_T && n_contrib && dL_dimage, "null input");
     const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     GsStageTimer timer(GS_STAGE_BLEND_BWD, stream);
-    k_blend_bwd<<<gx * gy, BL_THREADS, 0, stream>>>(image_width, image_height, reinterpret_cast<const float4 *>(rec), bg,
-                                                    compute_locally, reinterpret_cast<const uint2 *>(ranges), ids_sorted,
-                                                    final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity,
-                                                    dL_drgb);
+    k_blend_bwd<<<gx * gy * num_views, BL_THREADS, 0, stream>>>(
+        image_width, image_height, gx * gy, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
+        reinterpret_cast<const uint2 *>(ranges), ids_sorted, final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity,
+        dL_drgb);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

@@ -48,6 +48,25 @@ GS_D void gs_get_rect(float px, float py, int r, int gx, int gy, int &x0, int &y
     y1 = min(gy, max(0, (int)(__fdiv_rn(__fadd_rn(__fadd_rn(py, rr), (float)(GS_BLOCK_Y - 1)), (float)GS_BLOCK_Y))));
 }
 
+// ---- several views (cameras) binned and blended by ONE launch per stage --------------------------------
+// The splats of view v are rows [start[v], start[v+1]) of the concatenated splat arrays; its tiles are
+// [v*T, (v+1)*T) of the concatenated tile arrays (compute_locally, ranges) and of the sort key.  A rank that owns a
+// tile-row strip of each of the B cameras of a step (workload_division.py:852-941) bins and blends all of them
+// together; B = 1 is the reference's per-camera call.  Passed by value (kernel parameter space).
+struct GsViews {
+    int n;                          // number of views
+    int T;                          // tiles per view
+    int start[GS_MAX_VIEWS + 1];
+};
+GS_D int gs_view_of(const GsViews &v, int i) {  // largest k with start[k] <= i
+    int lo = 0, hi = v.n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (v.start[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // ---- mbarrier + TMA bulk copy (cp.async.bulk) wrappers -------------------------------------------
 GS_D uint32_t gs_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

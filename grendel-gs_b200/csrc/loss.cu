@@ -37,15 +37,30 @@ extern "C" size_t gs_loss_temp_bytes(int rows, int image_width) {
     return (size_t)9 * (size_t)(rows > 0 ? rows : 0) * (size_t)image_width * sizeof(float) + 256;
 }
 
-// temp layout: [0,16) two double accumulators; [256, ...) maps (3 maps x 3 channels x rows x W)
+// The strips of up to GS_MAX_VIEWS cameras handled by one launch (blockIdx.z = view); passed by value.
+struct LossViews {
+    int row0[GS_MAX_VIEWS], rows[GS_MAX_VIEWS];       // window rows [row0, row0+rows) of the view's image
+    int crow0[GS_MAX_VIEWS], crow1[GS_MAX_VIEWS];     // counted rows, relative to row0
+    const uint8_t *gt[GS_MAX_VIEWS];                  // (3, rows, W) uint8 ground truth of the window
+    unsigned long long map_off[GS_MAX_VIEWS];         // float offset of the view's 9 derivative planes in `maps`
+};
+
+// temp layout: [0,16) two double accumulators per view; then maps (3 maps x 3 channels x rows x W per view)
 __global__ void __launch_bounds__(LS_THREADS)
-k_loss_fwd(int W, int H, int row0, int rows, int crow0, int crow1, const float *__restrict__ image,
-           const uint8_t *__restrict__ gt, float *__restrict__ maps, double *__restrict__ sums) {
+k_loss_fwd(int W, int H, const LossViews lv, const float *__restrict__ image, float *__restrict__ maps,
+           double *__restrict__ sums) {
     __shared__ float s_x[LS_IN][LS_IN + 1], s_y[LS_IN][LS_IN + 1];
     __shared__ float s_h[5][LS_IN][LS_TILE + 1];
     __shared__ float s_red[2][LS_THREADS / 32];
+    const int view = blockIdx.z;
+    const int row0 = lv.row0[view], rows = lv.rows[view], crow0 = lv.crow0[view], crow1 = lv.crow1[view];
     const int tx0 = blockIdx.x * LS_TILE, ty0 = blockIdx.y * LS_TILE;  // strip-local tile origin
+    if (ty0 >= rows) return;  // the grid is sized for the tallest strip of the batch
     const size_t HW = (size_t)H * W, SW = (size_t)rows * W;
+    const uint8_t *__restrict__ gt = lv.gt[view];
+    image += (size_t)view * 3 * HW;
+    maps += lv.map_off[view];
+    sums += 2 * view;
     const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
     float l1 = 0.f, ss = 0.f;
     for (int ch = 0; ch < 3; ch++) {
@@ -133,21 +148,27 @@ k_loss_fwd(int W, int H, int row0, int rows, int crow0, int crow1, const float *
     }
 }
 
-__global__ void k_loss_finalize(const double *__restrict__ sums, double inv_norm, float *__restrict__ out) {
-    out[0] = (float)(sums[0] * inv_norm);
-    out[1] = (float)(sums[1] * inv_norm);
+__global__ void k_loss_finalize(int n, const double *__restrict__ sums, double inv_norm, float *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;  // 2 values (Ll1, ssim) per view
+    if (k < 2 * n) out[k] = (float)(sums[k] * inv_norm);
 }
 
 __global__ void __launch_bounds__(LS_THREADS)
-k_loss_bwd(int W, int H, int row0, int rows, int crow0, int crow1, const float *__restrict__ image,
-           const uint8_t *__restrict__ gt,
-           const float *__restrict__ maps, const float *__restrict__ grad_l1, const float *__restrict__ grad_ssim,
-           float inv_norm, float *__restrict__ dimg) {
+k_loss_bwd(int W, int H, const LossViews lv, const float *__restrict__ image, const float *__restrict__ maps,
+           const float *__restrict__ grad_l1, const float *__restrict__ grad_ssim, float inv_norm,
+           float *__restrict__ dimg) {
     __shared__ float s_m[3][LS_IN][LS_IN + 1];
     __shared__ float s_h[3][LS_IN][LS_TILE + 1];
+    const int view = blockIdx.z;
+    const int row0 = lv.row0[view], rows = lv.rows[view], crow0 = lv.crow0[view], crow1 = lv.crow1[view];
     const int tx0 = blockIdx.x * LS_TILE, ty0 = blockIdx.y * LS_TILE;
+    if (ty0 >= rows) return;
     const size_t HW = (size_t)H * W, SW = (size_t)rows * W;
-    const float gl1 = grad_l1[0] * inv_norm, gss = grad_ssim[0] * inv_norm;
+    const uint8_t *__restrict__ gt = lv.gt[view];
+    image += (size_t)view * 3 * HW;
+    dimg += (size_t)view * 3 * HW;
+    maps += lv.map_off[view];
+    const float gl1 = grad_l1[view] * inv_norm, gss = grad_ssim[view] * inv_norm;
     for (int ch = 0; ch < 3; ch++) {
         for (int k = threadIdx.x; k < LS_IN * LS_IN; k += LS_THREADS) {
             const int r = k / LS_IN, c = k % LS_IN;
@@ -208,58 +229,142 @@ k_loss_bwd(int W, int H, int row0, int rows, int crow0, int crow1, const float *
     }
 }
 
-extern "C" int gs_loss_forward(int image_height, int image_width, int row0, int row1, int count_row0, int count_row1,
-                               const float *image, const uint8_t *gt_u8, float *out_l1_ssim, void *temp,
-                               size_t temp_bytes, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int rows = row1 - row0;
-    GS_REQUIRE(image_height > 0 && image_width > 0 && row0 >= 0 && row1 <= image_height && rows > 0, "strip rows");
-    GS_REQUIRE(image && gt_u8 && out_l1_ssim && temp, "null pointer");
-    GS_REQUIRE(count_row0 >= row0 && count_row1 <= row1 && count_row1 >= count_row0, "count rows must lie inside [row0,row1)");
-    if (temp_bytes < gs_loss_temp_bytes(rows, image_width)) {
+// bytes in front of the derivative maps: the per-view double accumulators (one view: the original 256-byte header)
+#define LS_HEADER_1 ((size_t)256)
+#define LS_HEADER_B ((size_t)(2 * sizeof(double) * GS_MAX_VIEWS))
+
+// rows4: (num_views, 4) HOST ints = row0, row1, count_row0, count_row1 per view; row1 == row0 skips the view.
+// Fills the kernel-side table; returns the tallest window in *max_rows and the total window rows in *sum_rows.
+static int make_loss_views(int num_views, int H, int W, const int32_t *rows4, const void *const *gts, LossViews &lv,
+                           int *max_rows, size_t *sum_rows) {
+    GS_REQUIRE(num_views >= 1 && num_views <= GS_MAX_VIEWS, "num_views must be in [1, GS_MAX_VIEWS]");
+    GS_REQUIRE(H > 0 && W > 0 && rows4 && gts, "sizes");
+    size_t off = 0;
+    int mx = 0;
+    for (int v = 0; v < GS_MAX_VIEWS; v++) {
+        lv.row0[v] = lv.rows[v] = lv.crow0[v] = lv.crow1[v] = 0;
+        lv.gt[v] = nullptr;
+        lv.map_off[v] = 0ull;
+        if (v >= num_views) continue;
+        const int row0 = rows4[4 * v], row1 = rows4[4 * v + 1], c0 = rows4[4 * v + 2], c1 = rows4[4 * v + 3];
+        const int rows = row1 - row0;
+        GS_REQUIRE(row0 >= 0 && row1 <= H && rows >= 0, "strip rows");
+        if (rows == 0) continue;
+        GS_REQUIRE(c0 >= row0 && c1 <= row1 && c1 >= c0, "count rows must lie inside [row0,row1)");
+        GS_REQUIRE(gts[v] != nullptr, "null ground-truth pointer");
+        lv.row0[v] = row0; lv.rows[v] = rows; lv.crow0[v] = c0 - row0; lv.crow1[v] = c1 - row0;
+        lv.gt[v] = (const uint8_t *)gts[v];
+        lv.map_off[v] = (unsigned long long)off;
+        off += (size_t)9 * rows * W;
+        mx = rows > mx ? rows : mx;
+    }
+    *max_rows = mx;
+    *sum_rows = off / ((size_t)9 * W);
+    return GS_OK;
+}
+
+static int loss_forward_impl(int num_views, int H, int W, const int32_t *rows4, const float *image, const void *const *gts,
+                             float *out, void *temp, size_t temp_bytes, size_t header, cudaStream_t stream) {
+    GS_REQUIRE(image && out && temp, "null pointer");
+    LossViews lv;
+    int max_rows = 0;
+    size_t sum_rows = 0;
+    int rc = make_loss_views(num_views, H, W, rows4, gts, lv, &max_rows, &sum_rows);
+    if (rc != GS_OK) return rc;
+    if (temp_bytes < header + (size_t)9 * sum_rows * W * sizeof(float)) {
         gs_set_error("gs_loss_forward: temp too small");
         return GS_ENOMEM;
     }
-    int rc = ensure_gauss();
+    rc = ensure_gauss();
     if (rc != GS_OK) return rc;
     double *sums = (double *)temp;
-    float *maps = (float *)((char *)temp + 256);
-    GS_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), stream));
-    dim3 grid((image_width + LS_TILE - 1) / LS_TILE, (rows + LS_TILE - 1) / LS_TILE);
+    float *maps = (float *)((char *)temp + header);
+    GS_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double) * (size_t)num_views, stream));
     GsStageTimer timer(GS_STAGE_LOSS_FWD, stream);
-    k_loss_fwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, count_row0 - row0, count_row1 - row0,
-                                                image, gt_u8, maps, sums);
-    GS_LAUNCH_CHECK();
-    k_loss_finalize<<<1, 1, 0, stream>>>(sums, 1.0 / (3.0 * (double)image_height * (double)image_width), out_l1_ssim);
+    if (max_rows > 0) {
+        dim3 grid((W + LS_TILE - 1) / LS_TILE, (max_rows + LS_TILE - 1) / LS_TILE, num_views);
+        k_loss_fwd<<<grid, LS_THREADS, 0, stream>>>(W, H, lv, image, maps, sums);
+        GS_LAUNCH_CHECK();
+    }
+    k_loss_finalize<<<1, 2 * GS_MAX_VIEWS, 0, stream>>>(num_views, sums, 1.0 / (3.0 * (double)H * (double)W), out);
     GS_LAUNCH_CHECK();
     return GS_OK;
+}
+
+static int loss_backward_impl(int num_views, int H, int W, const int32_t *rows4, const float *image,
+                              const void *const *gts, const void *temp, const float *grad_l1, const float *grad_ssim,
+                              float *dimg, size_t header, cudaStream_t stream) {
+    GS_REQUIRE(image && temp && grad_l1 && grad_ssim && dimg, "null pointer");
+    LossViews lv;
+    int max_rows = 0;
+    size_t sum_rows = 0;
+    int rc = make_loss_views(num_views, H, W, rows4, gts, lv, &max_rows, &sum_rows);
+    if (rc != GS_OK) return rc;
+    rc = ensure_gauss();
+    if (rc != GS_OK) return rc;
+    const float *maps = (const float *)((const char *)temp + header);
+    const size_t HW = (size_t)H * W;
+    // rows outside the windows carry no loss
+    if (num_views == 1) {
+        const int row0 = lv.row0[0], row1 = lv.row0[0] + lv.rows[0];
+        for (int ch = 0; ch < 3; ch++) {
+            if (row0 > 0) GS_CUDA_TRY(cudaMemsetAsync(dimg + ch * HW, 0, sizeof(float) * (size_t)row0 * W, stream));
+            if (row1 < H)
+                GS_CUDA_TRY(cudaMemsetAsync(dimg + ch * HW + (size_t)row1 * W, 0, sizeof(float) * (size_t)(H - row1) * W, stream));
+        }
+    } else if (sum_rows < (size_t)num_views * H) {
+        GS_CUDA_TRY(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * HW * (size_t)num_views, stream));
+    }
+    if (max_rows == 0) return GS_OK;
+    dim3 grid((W + LS_TILE - 1) / LS_TILE, (max_rows + LS_TILE - 1) / LS_TILE, num_views);
+    GsStageTimer timer(GS_STAGE_LOSS_BWD, stream);
+    k_loss_bwd<<<grid, LS_THREADS, 0, stream>>>(W, H, lv, image, maps, grad_l1, grad_ssim,
+                                                (float)(1.0 / (3.0 * (double)H * (double)W)), dimg);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_loss_forward(int image_height, int image_width, int row0, int row1, int count_row0, int count_row1,
+                               const float *image, const uint8_t *gt_u8, float *out_l1_ssim, void *temp,
+                               size_t temp_bytes, void *stream_) {
+    GS_REQUIRE(row1 > row0, "strip rows");
+    GS_REQUIRE(gt_u8, "null pointer");
+    const int32_t rows4[4] = {row0, row1, count_row0, count_row1};
+    const void *gts[1] = {gt_u8};
+    return loss_forward_impl(1, image_height, image_width, rows4, image, gts, out_l1_ssim, temp, temp_bytes, LS_HEADER_1,
+                             (cudaStream_t)stream_);
+}
+
+extern "C" size_t gs_loss_temp_bytes_batched(int num_views, const int32_t *rows4_host, int image_width) {
+    size_t rows = 0;
+    for (int v = 0; v < num_views && rows4_host; v++) {
+        const int r = rows4_host[4 * v + 1] - rows4_host[4 * v];
+        rows += r > 0 ? (size_t)r : 0;
+    }
+    return LS_HEADER_B + (size_t)9 * rows * (size_t)(image_width > 0 ? image_width : 0) * sizeof(float) + 256;
+}
+
+extern "C" int gs_loss_forward_batched(int num_views, int image_height, int image_width, const int32_t *rows4_host,
+                                       const float *image, const void *const *gt_u8_ptrs_host, float *out_l1_ssim,
+                                       void *temp, size_t temp_bytes, void *stream_) {
+    return loss_forward_impl(num_views, image_height, image_width, rows4_host, image, gt_u8_ptrs_host, out_l1_ssim, temp,
+                             temp_bytes, LS_HEADER_B, (cudaStream_t)stream_);
 }
 
 extern "C" int gs_loss_backward(int image_height, int image_width, int row0, int row1, int count_row0, int count_row1,
                                 const float *image, const uint8_t *gt_u8, const void *temp, const float *grad_l1,
                                 const float *grad_ssim, float *dL_dimage, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int rows = row1 - row0;
-    GS_REQUIRE(image_height > 0 && image_width > 0 && row0 >= 0 && row1 <= image_height && rows > 0, "strip rows");
-    GS_REQUIRE(image && gt_u8 && temp && grad_l1 && grad_ssim && dL_dimage, "null pointer");
-    GS_REQUIRE(count_row0 >= row0 && count_row1 <= row1 && count_row1 >= count_row0, "count rows must lie inside [row0,row1)");
-    int rc = ensure_gauss();
-    if (rc != GS_OK) return rc;
-    const float *maps = (const float *)((const char *)temp + 256);
-    const size_t HW = (size_t)image_height * image_width;
-    // rows outside the strip carry no loss
-    for (int ch = 0; ch < 3; ch++) {
-        if (row0 > 0) GS_CUDA_TRY(cudaMemsetAsync(dL_dimage + ch * HW, 0, sizeof(float) * (size_t)row0 * image_width, stream));
-        if (row1 < image_height)
-            GS_CUDA_TRY(cudaMemsetAsync(dL_dimage + ch * HW + (size_t)row1 * image_width, 0,
-                                        sizeof(float) * (size_t)(image_height - row1) * image_width, stream));
-    }
-    dim3 grid((image_width + LS_TILE - 1) / LS_TILE, (rows + LS_TILE - 1) / LS_TILE);
-    GsStageTimer timer(GS_STAGE_LOSS_BWD, stream);
-    k_loss_bwd<<<grid, LS_THREADS, 0, stream>>>(image_width, image_height, row0, rows, count_row0 - row0, count_row1 - row0,
-                                                image, gt_u8, maps, grad_l1,
-                                                grad_ssim, (float)(1.0 / (3.0 * (double)image_height * (double)image_width)),
-                                                dL_dimage);
-    GS_LAUNCH_CHECK();
-    return GS_OK;
+    GS_REQUIRE(row1 > row0, "strip rows");
+    GS_REQUIRE(gt_u8, "null pointer");
+    const int32_t rows4[4] = {row0, row1, count_row0, count_row1};
+    const void *gts[1] = {gt_u8};
+    return loss_backward_impl(1, image_height, image_width, rows4, image, gts, temp, grad_l1, grad_ssim, dL_dimage,
+                              LS_HEADER_1, (cudaStream_t)stream_);
+}
+
+extern "C" int gs_loss_backward_batched(int num_views, int image_height, int image_width, const int32_t *rows4_host,
+                                        const float *image, const void *const *gt_u8_ptrs_host, const void *temp,
+                                        const float *grad_l1, const float *grad_ssim, float *dL_dimage, void *stream_) {
+    return loss_backward_impl(num_views, image_height, image_width, rows4_host, image, gt_u8_ptrs_host, temp, grad_l1,
+                              grad_ssim, dL_dimage, LS_HEADER_B, (cudaStream_t)stream_);
 }

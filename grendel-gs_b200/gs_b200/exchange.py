@@ -20,6 +20,12 @@ import torch.distributed as dist
 from . import _lib, ops
 
 ROW, GROW = 11, 9
+TRACE = None   # diagnostics: callable(name) that synchronises and charges the time since the last mark (pipeline._mark)
+
+
+def _t(name):
+    if TRACE is not None:
+        TRACE(name)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -118,10 +124,21 @@ def _slab_ptrs(t, B):
     return (C.c_void_p * B)(*[base + k * step for k in range(B)])
 
 
+def _row_ptrs(t, starts, B):
+    """Device pointers of rows starts[k] (k < B) of a contiguous (N, ...) tensor; NULLs if t is None."""
+    if t is None:
+        return (C.c_void_p * B)(*[None] * B)
+    step = t.stride(0) * t.element_size() if t.shape[0] > 0 else 0
+    base = t.data_ptr()
+    return (C.c_void_p * B)(*[base + starts[k] * step for k in range(B)])
+
+
 class _ExchangeSplats(torch.autograd.Function):
     """inputs: means2D (B,P,2), rgb (B,P,3), conic_opacity (B,P,4) of the local shard for the B cameras.
-    outputs: (means2D, rgb, conic_opacity) received per camera (differentiable), then (radii, depths) per camera.
-    The backward returns whole (B,P,.) gradient tensors, so nothing is sliced or re-accumulated per camera."""
+    outputs: the received splats of all B cameras CONCATENATED in camera order -- means2D (N,2), rgb (N,3),
+    conic_opacity (N,4) (differentiable), radii (N) int32, depths (N); camera k owns rows
+    [view_start[k], view_start[k+1]).  That is the layout the batched render consumes, and it makes both directions
+    whole-tensor operations: nothing is sliced, concatenated or re-accumulated per camera."""
 
     @staticmethod
     def forward(ctx, state, m2, rgb, co):
@@ -134,41 +151,43 @@ class _ExchangeSplats(torch.autograd.Function):
         send = torch.empty((max(layout.total_send, 1), ROW), dtype=torch.float32, device=dev)
         _lib.call("gs_xchg_pack", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), _slab_ptrs(m2, B),
                   _slab_ptrs(rgb, B), _slab_ptrs(co, B), _slab_ptrs(radii, B), _slab_ptrs(depths, B), send.data_ptr(), s)
+        _t("x3 pack")
         recv = torch.empty((max(layout.total_recv, 1), ROW), dtype=torch.float32, device=dev)
         all_to_all_single(recv[:layout.total_recv], send[:layout.total_send], layout.recv_splits, layout.send_splits, group)
-        om2 = [torch.empty((n, 2), dtype=torch.float32, device=dev) for n in layout.n_recv]
-        orgb = [torch.empty((n, 3), dtype=torch.float32, device=dev) for n in layout.n_recv]
-        oco = [torch.empty((n, 4), dtype=torch.float32, device=dev) for n in layout.n_recv]
-        orad = [torch.empty((n,), dtype=torch.int32, device=dev) for n in layout.n_recv]
-        odep = [torch.empty((n,), dtype=torch.float32, device=dev) for n in layout.n_recv]
+        _t("x4 all_to_all")
+        vs = state["view_start"]
+        N = vs[B]
+        om2 = torch.empty((N, 2), dtype=torch.float32, device=dev)
+        orgb = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        oco = torch.empty((N, 4), dtype=torch.float32, device=dev)
+        orad = torch.empty((N,), dtype=torch.int32, device=dev)
+        odep = torch.empty((N,), dtype=torch.float32, device=dev)
         rs, ln, cam, ds = state["segs"]
         _lib.call("gs_xchg_unpack", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, recv.data_ptr(),
-                  B, _ptrs(om2), _ptrs(orgb), _ptrs(oco), _ptrs(orad), _ptrs(odep), s)
+                  B, _row_ptrs(om2, vs, B), _row_ptrs(orgb, vs, B), _row_ptrs(oco, vs, B), _row_ptrs(orad, vs, B),
+                  _row_ptrs(odep, vs, B), s)
         ctx.state = state
-        outs = []
-        for k in range(B):
-            outs += [om2[k], orgb[k], oco[k]]
-        auxs = []
-        for k in range(B):
-            auxs += [orad[k], odep[k]]
-        ctx.mark_non_differentiable(*auxs)
-        return tuple(outs + auxs)
+        ctx.mark_non_differentiable(orad, odep)
+        return om2, orgb, oco, orad, odep
 
     @staticmethod
-    def backward(ctx, *grads):
+    def backward(ctx, g_m2, g_rgb, g_co, *_unused):
         state = ctx.state
         layout, group = state["layout"], state["group"]
         B, P, W = state["B"], state["P"], state["W"]
         dev = state["flags"].device
         s = ops._stream()
-        g = [None if t is None else t.contiguous() for t in grads[:3 * B]]
+        vs = state["view_start"]
+        _t("b1 loss+render backward")
+        g_m2, g_rgb, g_co = (None if t is None else t.contiguous() for t in (g_m2, g_rgb, g_co))
         grecv = torch.empty((max(layout.total_recv, 1), GROW), dtype=torch.float32, device=dev)
         rs, ln, cam, ds = state["segs"]
         _lib.call("gs_xchg_pack_grad", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, B,
-                  _ptrs([g[3 * k] for k in range(B)]), _ptrs([g[3 * k + 1] for k in range(B)]),
-                  _ptrs([g[3 * k + 2] for k in range(B)]), grecv.data_ptr(), s)
+                  _row_ptrs(g_m2, vs, B), _row_ptrs(g_rgb, vs, B), _row_ptrs(g_co, vs, B), grecv.data_ptr(), s)
+        _t("b2 pack_grad")
         gsend = torch.empty((max(layout.total_send, 1), GROW), dtype=torch.float32, device=dev)
         all_to_all_single(gsend[:layout.total_send], grecv[:layout.total_recv], layout.send_splits, layout.recv_splits, group)
+        _t("b3 all_to_all")
         d_m2 = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
         d_rgb = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
         d_co = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
@@ -178,10 +197,25 @@ class _ExchangeSplats(torch.autograd.Function):
 
 
 def exchange(means2D, rgb, conic_opacity, radii, depths, strategies, settings, world, me, group=None):
+    """Per-camera view of exchange_cat (the reference's return shape, gaussian_renderer/__init__.py:1010-1023):
+    a list of B tuples (means2D, rgb, conic_opacity, radii, depths) -- row slices of the concatenated tensors, empty
+    where this rank renders no strip of the camera -- and the all-gathered counts."""
+    (m2, c3, co, rad, dep), view_start, cnt = exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies,
+                                                           settings, world, me, group)
+    out = []
+    for k in range(len(view_start) - 1):
+        a, b = view_start[k], view_start[k + 1]
+        out.append((m2[a:b], c3[a:b], co[a:b], rad[a:b], dep[a:b]))
+    return out, cnt
+
+
+def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, settings, world, me, group=None):
     """means2D (B,P,2), rgb (B,P,3), conic_opacity (B,P,4), radii (B,P) int32, depths (B,P): the local shard projected
     into the B cameras of the step (ops.preprocess_gaussians_batched, or torch.stack of per-camera results).
-    Returns per camera the redistributed tuple (means2D, rgb, conic_opacity, radii, depths) for the strip this rank
-    renders (empty tensors if none), and the all-gathered counts cnt[i][k][j] (the reference's gpui_to_gpuj_imgk_size)."""
+    Returns ((means2D (N,2), rgb (N,3), conic_opacity (N,4), radii (N), depths (N)), view_start, cnt): the splats this
+    rank has to render, all cameras concatenated in camera order (camera k = rows [view_start[k], view_start[k+1]),
+    none if the rank renders no strip of it), and the all-gathered counts cnt[i][k][j] (the reference's
+    gpui_to_gpuj_imgk_size)."""
     B, P = means2D.shape[0], means2D.shape[1]
     dev = means2D.device
     H, Wimg = int(settings[0].image_height), int(settings[0].image_width)
@@ -200,14 +234,14 @@ def exchange(means2D, rgb, conic_opacity, radii, depths, strategies, settings, w
     temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
     _lib.call("gs_xchg_route", B, P, world, H, Wimg, _slab_ptrs(m2d, B), _slab_ptrs(radii, B), _i32(lo), _i32(hi),
               flags.data_ptr(), gpos.data_ptr(), counts.data_ptr(), temp.data_ptr(), tb, ops._stream())
+    _t("x1 route")
     cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]
+    _t("x2 gather counts")
     layout = Layout(cnt, me, [st.gpu_ids for st in strategies])
+    view_start = [0]
+    for n in layout.n_recv:
+        view_start.append(view_start[-1] + n)
     state = dict(layout=layout, group=group, radii=radii, depths=depths, flags=flags, gpos=gpos, B=B, P=P, W=world,
-                 segs=segments(layout))
+                 segs=segments(layout), view_start=view_start)
     res = _ExchangeSplats.apply(state, means2D, rgb, conic_opacity)
-    out = []
-    for k in range(B):
-        m2, c3, co = res[3 * k:3 * k + 3]
-        rad, dep = res[3 * B + 2 * k:3 * B + 2 * k + 2]
-        out.append((m2, c3, co, rad, dep))
-    return out, cnt
+    return res, view_start, cnt

@@ -306,6 +306,163 @@ def render_gaussians(means2D, conic_opacity, rgb, depths, radii, compute_locally
     return _RenderGaussians.apply(means2D, conic_opacity, rgb, depths, radii, compute_locally, raster_settings, collector)
 
 
+MAX_VIEWS = 64   # GS_MAX_VIEWS
+
+
+def _i32_array(vals):
+    return (C.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+class _RenderGaussiansBatched(torch.autograd.Function):
+    """render_gaussians for the B cameras of a batch in ONE pass (gs_render_*_batched): the splats of all cameras
+    concatenated (camera k = rows [view_start[k], view_start[k+1])), masks (B,T), images (B,3,H,W)."""
+
+    @staticmethod
+    def forward(ctx, means2D, conic_opacity, rgb, depths, radii, compute_locally, view_start, rs, collector):
+        means2D, conic_opacity, rgb = _f32c(means2D, "means2D"), _f32c(conic_opacity, "conic_opacity"), _f32c(rgb, "rgb")
+        depths = _f32c(depths, "depths")
+        if radii.dtype != torch.int32:
+            radii = radii.to(torch.int32)
+        radii = radii.contiguous()
+        B = len(view_start) - 1
+        P = int(view_start[B])
+        if not 1 <= B <= MAX_VIEWS:
+            raise ValueError(f"1..{MAX_VIEWS} views per batched render, got {B}")
+        if means2D.shape[0] != P:
+            raise ValueError(f"view_start ends at {P} but {means2D.shape[0]} splats were passed")
+        H, W = int(rs.image_height), int(rs.image_width)
+        ty, tx = _tiles(rs)
+        T = ty * tx
+        dev = means2D.device
+        if compute_locally is None:
+            cl = torch.ones((B * T,), dtype=torch.uint8, device=dev)
+        else:
+            if compute_locally.numel() != B * T:
+                raise ValueError(f"compute_locally must have {B}x{ty}x{tx} entries, got {tuple(compute_locally.shape)}")
+            cl = compute_locally.contiguous()
+            cl = cl.view(torch.uint8) if cl.dtype == torch.bool else cl.to(torch.uint8)
+        bg = _f32c(rs.bg, "bg")
+        s = _stream()
+        vs = _i32_array(view_start)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        offsets = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
+        order = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
+        rec = torch.empty((max(P, 1), 12), dtype=torch.float32, device=dev)
+        tb = _lib.query("gs_render_count_temp_bytes", P)
+        temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
+        R = C.c_int64(0)
+        _lib.call("gs_render_count_batched", B, vs, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
+                  depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(),
+                  rec.data_ptr(), temp.data_ptr(), tb, C.byref(R), s)
+        R = int(R.value)
+        global LAST_R_TOTAL
+        LAST_R_TOTAL += R
+        Ra = max(R, 1)
+        tiles = torch.empty((2, Ra), dtype=torch.int32, device=dev)
+        ids = torch.empty((2, Ra), dtype=torch.int32, device=dev)
+        sb = _lib.query("gs_render_sort_temp_bytes", R)
+        sort_temp = torch.empty((sb,), dtype=torch.uint8, device=dev)
+        ranges = torch.empty((B * T, 2), dtype=torch.int32, device=dev)
+        image = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        final_T = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        n_contrib = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+        stats = torch.empty((B, 3), dtype=torch.int64, device=dev)
+        _lib.call("gs_render_forward_batched", B, vs, R, H, W, means2D.data_ptr(), radii.data_ptr(), cl.data_ptr(),
+                  order.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), tiles[0].data_ptr(),
+                  ids[0].data_ptr(), tiles[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(),
+                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), s)
+        ev1.record()
+        _timed(collector, "forward_render_time", ev0, ev1)
+        ids_sorted = ids[1].clone() if R > 0 else ids[1]  # let the 2R-entry scratch go back to the allocator
+        ctx.rs, ctx.R, ctx.P, ctx.B, ctx.collector = rs, R, P, B, collector
+        ctx.save_for_backward(rec, bg, cl, ranges, ids_sorted, final_T, n_contrib)
+        ctx.mark_non_differentiable(stats)
+        return image, stats
+
+    @staticmethod
+    def backward(ctx, g_image, _g_stats):
+        rec, bg, cl, ranges, ids_sorted, final_T, n_contrib = ctx.saved_tensors
+        rs, R, P, B = ctx.rs, ctx.R, ctx.P, ctx.B
+        H, W = int(rs.image_height), int(rs.image_width)
+        dev = rec.device
+        g_image = torch.zeros((B, 3, H, W), dtype=torch.float32, device=dev) if g_image is None else _f32c(g_image, "grad")
+        d_means2D = torch.empty((P, 2), dtype=torch.float32, device=dev)
+        d_conic = torch.empty((P, 4), dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.call("gs_render_backward_batched", B, P, R, H, W, rec.data_ptr(), bg.data_ptr(), cl.data_ptr(),
+                  ranges.data_ptr(), ids_sorted.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), g_image.data_ptr(),
+                  d_means2D.data_ptr(), d_conic.data_ptr(), d_rgb.data_ptr(), _stream())
+        ev1.record()
+        _timed(ctx.collector, "backward_render_time", ev0, ev1)
+        return d_means2D, d_conic, d_rgb, None, None, None, None, None, None
+
+
+def render_gaussians_batched(means2D, conic_opacity, rgb, depths, radii, compute_locally, view_start, raster_settings,
+                             cuda_args=None):
+    """All B cameras of a batch in one pass.  means2D (N,2), conic_opacity (N,4), rgb (N,3), depths (N), radii (N):
+    the splats of the B cameras concatenated, camera k = rows [view_start[k], view_start[k+1]) (len(view_start) = B+1);
+    compute_locally (B, TILE_Y*TILE_X) (None = everything local); the cameras share the image size and background of
+    `raster_settings` (their view / projection matrices were consumed by the preprocess).
+    -> (images (B,3,H,W) with non-local tiles exactly 0, stats (B,3) int64 = n_render / n_consider / n_contrib)."""
+    collector = None
+    if isinstance(cuda_args, dict):
+        collector = cuda_args.setdefault("stats_collector", {})
+    return _RenderGaussiansBatched.apply(means2D, conic_opacity, rgb, depths, radii, compute_locally,
+                                         [int(v) for v in view_start], raster_settings, collector)
+
+
+class _FusedL1SSIMBatched(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, gts, rows4):
+        images = _f32c(images, "images")
+        B, _, H, W = images.shape
+        if len(gts) != B or len(rows4) != B:
+            raise ValueError("one ground-truth strip and one (row0,row1,count_row0,count_row1) per view")
+        keep = []
+        for k, (gt, r) in enumerate(zip(gts, rows4)):
+            rows = int(r[1]) - int(r[0])
+            if rows == 0:
+                keep.append(None)
+                continue
+            if gt is None or gt.dtype != torch.uint8 or not gt.is_cuda:
+                raise TypeError("gt strips must be CUDA uint8 tensors (3, rows, W)")
+            gt = gt.contiguous()
+            if tuple(gt.shape) != (3, rows, W):
+                raise ValueError(f"gt strip {k} must be (3,{rows},{W}), got {tuple(gt.shape)}")
+            keep.append(gt)
+        flat = _i32_array([int(v) for r in rows4 for v in r])
+        gptr = (C.c_void_p * B)(*[None if g is None else g.data_ptr() for g in keep])
+        tb = _lib.query("gs_loss_temp_bytes_batched", B, flat, W)
+        temp = torch.empty((tb,), dtype=torch.uint8, device=images.device)
+        out = torch.empty((B, 2), dtype=torch.float32, device=images.device)
+        _lib.call("gs_loss_forward_batched", B, H, W, flat, images.data_ptr(), gptr, out.data_ptr(), temp.data_ptr(), tb,
+                  _stream())
+        ctx.rows4, ctx.gts = flat, keep
+        ctx.save_for_backward(images, temp)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        images, temp = ctx.saved_tensors
+        B, _, H, W = images.shape
+        g_l1, g_ssim = g_out[:, 0].to(torch.float32).contiguous(), g_out[:, 1].to(torch.float32).contiguous()
+        d_images = torch.empty_like(images)
+        gptr = (C.c_void_p * B)(*[None if g is None else g.data_ptr() for g in ctx.gts])
+        _lib.call("gs_loss_backward_batched", B, H, W, ctx.rows4, images.data_ptr(), gptr, temp.data_ptr(),
+                  g_l1.data_ptr(), g_ssim.data_ptr(), d_images.data_ptr(), _stream())
+        return d_images, None, None
+
+
+def fused_l1_ssim_batched(images, gts_u8, rows4):
+    """The strip losses of the B cameras of a batch in one launch.  images (B,3,H,W); gts_u8: list of B CUDA uint8
+    strips (3,rows,W) (None where rows == 0); rows4: B tuples (row0, row1, count_row0, count_row1).
+    -> (B,2) = (Ll1, ssim_loss) per camera, both normalised by 3*H*W; zeros for cameras without rows."""
+    return _FusedL1SSIMBatched.apply(images, list(gts_u8), [tuple(int(v) for v in r) for r in rows4])
+
+
 def get_local2j_ids_bool(image_height, image_width, rank, world_size, means2D, radii, dist_global_strategy,
                          cuda_args=None):
     """(P, world_size) bool: does splat i touch rank j's flattened tile range.  `rank` is unused (kept for

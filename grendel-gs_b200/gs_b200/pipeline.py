@@ -113,9 +113,12 @@ class Trainer:
     """
 
     def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None,
-                 fused_activations=True, border_exchange=False):
+                 fused_activations=True, border_exchange=False, batched_render=True):
         from . import exchange as _ex
         self._ex = _ex
+        # bin + blend + loss of all B cameras in one pass (ops.render_gaussians_batched) instead of the reference's
+        # per-camera loop (render_final, gaussian_renderer/__init__.py:1217-1288); False keeps the per-camera calls
+        self.batched_render = batched_render
         self.device, self.rank, self.world, self.group = device, rank, world, group
         self.lambda_dssim = lambda_dssim
         self.fused_activations = fused_activations
@@ -134,6 +137,8 @@ class Trainer:
         self._cams_packed = None   # (B,40) camera table of the batched preprocess (cameras are fixed per Trainer)
         self._strategy_cache = None
         self._mask_cache = {}
+        self._bmask_cache = {}
+        self._n_renders = 0
         self._copy_stream = None
         self._loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
         self._info = {}
@@ -167,6 +172,7 @@ class Trainer:
         memory inside the step and reads the loss back (the end-to-end leg); returns the loss as a float then."""
         import os as _os, time as _time
         self._trace_on = _os.environ.get("GS_B200_TRACE") == "1"
+        self._ex.TRACE = self._mark if self._trace_on else None
         if self._trace_on:
             if not hasattr(self, "trace"):
                 self.trace = {}
@@ -209,6 +215,8 @@ class Trainer:
             xyz, scaling, rotation, feats, opacity = p.get_xyz, p.get_scaling, p.get_rotation, p.get_features, p.get_opacity
         collectors = [{} for _ in self.dcams]
         screen = []
+        B = len(settings)
+        use_batched = self.batched_render and B > 1 and not self.border_exchange
         if self.fused_activations and len(settings) > 1:
             # all B cameras in ONE launch: every Gaussian is read once and projected into each camera
             if self._cams_packed is None:
@@ -218,7 +226,7 @@ class Trainer:
                 self.W, self.H, p.active_sh_degree)
             bm2.retain_grad()   # (B,P,2): densification reads bm2.grad[k] (means2D.grad of camera k, densification.py:24)
             batched = (bm2, brgb, bco, bradii, bdepths)
-            if self.world == 1:
+            if self.world == 1 and not use_batched:
                 for k in range(len(settings)):
                     screen.append((bm2[k], brgb[k], bco[k], bradii[k], bdepths[k]))
             settings_loop = []
@@ -235,21 +243,76 @@ class Trainer:
             out[0].retain_grad()
             screen.append(out)
         self.means2D = batched[0] if batched is not None else [s[0] for s in screen]
-        self._mark("preprocess")
+        self._mark("p preprocess")
+        if batched is None and (self.world > 1 or use_batched):
+            # per-camera results (B == 1 or unfused activations): stack into (B,P,.)
+            batched = tuple(torch.stack([s[q] for s in screen]) for q in range(5))
+        cat = view_start = None
         if self.world > 1:
-            if batched is None:   # per-camera results (B == 1 or unfused activations): stack into (B,P,.)
-                batched = tuple(torch.stack([s[q] for s in screen]) for q in range(5))
-            redistributed, cnt = self._ex.exchange(*batched, strategies, settings, self.world, self.rank, self.group)
+            if use_batched:
+                cat, view_start, cnt = self._ex.exchange_cat(*batched, strategies, settings, self.world, self.rank,
+                                                             self.group)
+            else:
+                redistributed, cnt = self._ex.exchange(*batched, strategies, settings, self.world, self.rank, self.group)
+        elif use_batched:   # (B,P,.) stacked IS the concatenation: camera k = rows [k P, (k+1) P)
+            Pn = batched[0].shape[1]
+            cat = (batched[0].reshape(-1, 2), batched[1].reshape(-1, 3), batched[2].reshape(-1, 4),
+                   batched[3].reshape(-1), batched[4].reshape(-1))
+            view_start = [k * Pn for k in range(B + 1)]
         else:
             redistributed = screen
         self._radii_local = batched[3] if batched is not None else torch.stack([s[3] for s in screen])
-        self._mark("exchange")
+        self._mark("x5 unpack")
         loss_sum = None
         Vp = Pl = 0
-        for k, st in enumerate(strategies):
+        self._n_renders = 0
+        if use_batched:
+            mk = tuple((tuple(st.gpu_ids), tuple(st.division_pos), st.rank) for st in strategies)
+            if mk not in self._bmask_cache:
+                m = torch.zeros((B, self.tile_y, self.tile_x), dtype=torch.uint8, device=self.device)
+                rows4, coef, const = [], [], 0.0
+                for k, st in enumerate(strategies):
+                    r = st.local_rows()
+                    if r is None:   # no strip of this camera here: no tiles, no loss term
+                        rows4.append((0, 0, 0, 0))
+                        coef += [0.0, 0.0]
+                        continue
+                    m[k, r[0]:r[1]] = 1
+                    y0, y1 = st.local_pixel_rows(self.H)
+                    rows4.append((y0, y1, y0, y1))
+                    coef += [1.0 - self.lambda_dssim, -self.lambda_dssim]
+                    const += self.lambda_dssim
+                self._bmask_cache[mk] = (m.reshape(B, -1), rows4,
+                                         torch.tensor(coef, dtype=torch.float32, device=self.device), const)
+            cl, rows4, coef, const = self._bmask_cache[mk]
+            m2, rgb, co, radii, depths = cat
+            images, _stats = ops_.render_gaussians_batched(m2, co, rgb, depths, radii, cl, view_start, settings[0],
+                                                           {"stats_collector": collectors[0]})
+            self._n_renders = 1
+            gts = []
+            for k, (y0, y1, _c0, _c1) in enumerate(rows4):
+                if y1 == y0:
+                    gts.append(None)
+                elif resident:
+                    gts.append(self._gt_strip(k, y0, y1, True))
+                else:
+                    gt, ev = gt_ready[k]
+                    torch.cuda.current_stream().wait_event(ev)
+                    gt.record_stream(torch.cuda.current_stream())
+                    gts.append(gt)
+            l1_ssim = ops_.fused_l1_ssim_batched(images, gts, rows4)
+            # sum over the local strips of (1 - lambda) Ll1 + lambda (1 - ssim)
+            loss_sum = torch.dot(l1_ssim.reshape(-1), coef) + const
+            Vp = int(view_start[-1])
+            Pl = sum((r[1] - r[0]) * self.W for r in rows4)
+            strategies_loop = []
+        else:
+            strategies_loop = strategies
+        for k, st in enumerate(strategies_loop):
             rows = st.local_rows()
             if rows is None:
                 continue
+            self._n_renders += 1
             m2, rgb, co, radii, depths = redistributed[k]
             ck = (tuple(st.gpu_ids), tuple(st.division_pos), st.rank)
             if ck not in self._mask_cache:
@@ -274,9 +337,9 @@ class Trainer:
             loss_sum = loss if loss_sum is None else loss_sum + loss
             Vp += m2.shape[0]
             Pl += (y1 - y0) * self.W
-        self._mark("render+loss")
+        self._mark("r render+loss")
         loss_sum.backward()
-        self._mark("backward")
+        self._mark("b4 backward (rest)")
         self._collectors, self._strategies = collectors, strategies
         self._counts = dict(Vp=Vp, P_local=Pl)
         if resident:
@@ -294,5 +357,4 @@ class Trainer:
     def io_bytes_per_step(self):
         """(host->device, device->host) bytes of the last resident=False step: GT strips in, loss out
         (+ the 8-byte instance count each render reads back)."""
-        renders = sum(1 for st in self._strategies if st.local_rows() is not None)
-        return int(self._h2d), 4 + 8 * renders
+        return int(self._h2d), 4 + 8 * self._n_renders

@@ -176,6 +176,38 @@ GS_API int gs_render_backward(int P, int64_t R, int image_height, int image_widt
                        const float *final_T, const uint32_t *n_contrib, const float *dL_dimage, float *dL_dmeans2D,
                        float *dL_dconic_opacity, float *dL_drgb, void *stream);
 
+/* ---- the same three calls for ALL cameras of a training batch at once --------------------------------------
+ * The reference loops over the B cameras of a batch and calls render_gaussians once per camera
+ * (render_final, gaussian_renderer/__init__.py:1217-1288, called at train_internal.py:178); with the pixels of every camera cut into
+ * W strips each of those calls works on 1/W of an image, so at W = 8 a rank issues 8 x ~12 small launches and waits
+ * 8 times for an instance count.  These entry points bin and blend the strips of all B cameras in ONE pass:
+ *   - the splats of the B cameras are concatenated: camera v owns rows [view_start[v], view_start[v+1]) of
+ *     means2D / conic_opacity / rgb / depths / radii (view_start: HOST int32[num_views+1], view_start[0] = 0);
+ *   - compute_locally is (B, TILE_Y*TILE_X), ranges (B*T, 2), the sort key is v*T + tile;
+ *   - image (B,3,H,W), final_T (B,H,W), n_contrib (B,H,W), stats (B,3) or NULL, dL_dimage (B,3,H,W);
+ *   - order / offsets / rec / ids index the concatenated splat rows, the gradients are (P,2) (P,4) (P,3) with
+ *     P = view_start[num_views].
+ * Per camera the result is bit-identical to the single-camera call (same instance order within every tile).
+ * num_views <= GS_MAX_VIEWS; scratch sizes are those of the single-camera calls with P and R totals. */
+#define GS_MAX_VIEWS 64
+GS_API int gs_render_count_batched(int num_views, const int32_t *view_start_host, int image_height, int image_width,
+                                   const float *means2D, const float *conic_opacity, const float *rgb,
+                                   const float *depths, const int32_t *radii, const uint8_t *compute_locally,
+                                   uint32_t *order, uint32_t *offsets, float *rec, void *temp, size_t temp_bytes,
+                                   int64_t *R_host, void *stream);
+GS_API int gs_render_forward_batched(int num_views, const int32_t *view_start_host, int64_t R, int image_height,
+                                     int image_width, const float *means2D, const int32_t *radii,
+                                     const uint8_t *compute_locally, const uint32_t *order, const uint32_t *offsets,
+                                     const float *rec, const float *bg, uint32_t *tiles_unsorted, uint32_t *ids_unsorted,
+                                     uint32_t *tiles_sorted, uint32_t *ids_sorted, void *sort_temp,
+                                     size_t sort_temp_bytes, uint32_t *ranges, float *image, float *final_T,
+                                     uint32_t *n_contrib, int64_t *stats, void *stream);
+GS_API int gs_render_backward_batched(int num_views, int P, int64_t R, int image_height, int image_width,
+                                      const float *rec, const float *bg, const uint8_t *compute_locally,
+                                      const uint32_t *ranges, const uint32_t *ids_sorted, const float *final_T,
+                                      const uint32_t *n_contrib, const float *dL_dimage, float *dL_dmeans2D,
+                                      float *dL_dconic_opacity, float *dL_drgb, void *stream);
+
 /* ---- per-kernel device timing ------------------------------------------------------------------
  * The reference's fork logs per-stage GPU times under --zhx_time ("10 preprocess time: 0.29 ms", ...;
  * /root/reference/analyze_statistic.py:1972-1991).  When enabled, every launch site brackets its
@@ -229,6 +261,19 @@ GS_API int gs_loss_forward(int image_height, int image_width, int row0, int row1
 GS_API int gs_loss_backward(int image_height, int image_width, int row0, int row1, int count_row0, int count_row1,
                             const float *image, const uint8_t *gt_u8, const void *temp, const float *grad_l1,
                             const float *grad_ssim, float *dL_dimage, void *stream);
+
+/* The strip losses of all B cameras of a batch in one launch (the reference loops batched_loss over the cameras,
+ * loss_distribution.py:2588-2640).  rows4_host: HOST int32 (B,4) = row0, row1, count_row0, count_row1 per camera
+ * (row1 == row0: this rank renders no strip of that camera; its outputs are 0).  image / dL_dimage: (B,3,H,W);
+ * gt_u8_ptrs_host: HOST array of B device pointers to the (3,rows,W) uint8 strips; out_l1_ssim: (B,2);
+ * grad_l1 / grad_ssim: DEVICE (B).  Per camera the numbers are those of the single-camera calls. */
+GS_API size_t gs_loss_temp_bytes_batched(int num_views, const int32_t *rows4_host, int image_width);
+GS_API int gs_loss_forward_batched(int num_views, int image_height, int image_width, const int32_t *rows4_host,
+                                   const float *image, const void *const *gt_u8_ptrs_host, float *out_l1_ssim,
+                                   void *temp, size_t temp_bytes, void *stream);
+GS_API int gs_loss_backward_batched(int num_views, int image_height, int image_width, const int32_t *rows4_host,
+                                    const float *image, const void *const *gt_u8_ptrs_host, const void *temp,
+                                    const float *grad_l1, const float *grad_ssim, float *dL_dimage, void *stream);
 
 /* ---- all-to-all staging -- gaussian_renderer/__init__.py:590-607,651-658 --------------------------
  * Replaces the per-(destination, camera) nonzero() + index_select + torch.cat glue around the sparse

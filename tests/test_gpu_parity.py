@@ -382,6 +382,110 @@ def test_batched_preprocess_equals_per_camera():
         assert frac <= OUTLIER_FRAC, name
 
 
+def _grad_close(a, b, what):
+    a, b = a.double(), b.double()
+    tol = 2e-5 * b.abs() + 2e-5 * b.abs().mean()      # same pairs, different atomics order
+    frac = float(((a - b).abs() > tol).double().mean())
+    assert frac <= 1e-4, (what, frac)
+
+
+def test_batched_render_and_loss_equal_per_camera():
+    """gs_render_*_batched / gs_loss_*_batched over three cameras (ragged splat counts; one camera fully local, one a
+    strip of tile rows, one with NO local tile) against the single-camera calls: images, loss terms and image gradients
+    bit-identical, splat gradients equal up to the order of the atomics."""
+    from types import SimpleNamespace
+    from gs_b200 import ops
+    W, H = 300, 170
+    ty, tx = (H + 15) // 16, (W + 15) // 16
+    ns = [9000, 4001, 2500]
+    bg = torch.tensor([0.1, 0.3, 0.2], device="cuda")
+    rs = SimpleNamespace(image_height=H, image_width=W, bg=bg)
+    o = Oracle(np.float32)
+    pres, masks = [], []
+    for k, n in enumerate(ns):
+        cam, sc = case(n, W, H, seed=60 + k, radius_px=9.0, yaw=2.0 * k)
+        pres.append(o.preprocess_forward(sc["means3D"], sc["scales"], sc["rotations"], sc["shs"], sc["opacities"], cam))
+        m = torch.zeros((ty, tx), dtype=torch.uint8, device="cuda")
+        if k == 0:
+            m[:] = 1
+        elif k == 1:
+            m[3:7] = 1
+        masks.append(m)
+    rows4 = [(0, H, 0, H), (48, 112, 48, 112), (0, 0, 0, 0)]
+    gts = [torch.from_numpy(syn.make_gt_image(W, H, seed=70 + k)).cuda() for k in range(3)]
+    strips = [None if r[1] == r[0] else gts[k][:, r[0]:r[1]].contiguous() for k, r in enumerate(rows4)]
+    lam = 0.2
+
+    def leaves(k):
+        p = pres[k]
+        ts = [gu.to_dev(p[q]) for q in ("means2D", "conic_opacity", "rgb")]
+        for t in ts:
+            t.requires_grad_(True)
+        return ts, gu.to_dev(p["depths"]), gu.to_dev(p["radii"])
+
+    # ---- per camera -----------------------------------------------------------------------------------------
+    ref_img, ref_terms, ref_grads, ref_dimg = [], [], [], []
+    for k in range(3):
+        (m2, co, rgb), dep, rad = leaves(k)
+        img, *_ = ops.render_gaussians(m2, co, rgb, dep, rad, masks[k], rs)
+        img.retain_grad()
+        ref_img.append(img.detach().clone())
+        if strips[k] is None:
+            ref_terms.append(None)
+            ref_grads.append(None)
+            ref_dimg.append(None)
+            continue
+        l1, ss = ops.fused_l1_ssim(img, strips[k], rows4[k][0], rows4[k][1])
+        ((1 - lam) * l1 + lam * (1 - ss)).backward()
+        ref_terms.append((float(l1), float(ss)))
+        ref_grads.append((m2.grad.clone(), co.grad.clone(), rgb.grad.clone()))
+        ref_dimg.append(img.grad.clone())
+    # ---- batched ----------------------------------------------------------------------------------------------
+    L = [leaves(k) for k in range(3)]
+    cat = [torch.cat([L[k][0][q] for k in range(3)]) for q in range(3)]
+    dep, rad = torch.cat([l[1] for l in L]), torch.cat([l[2] for l in L])
+    vs = [0, ns[0], ns[0] + ns[1], sum(ns)]
+    imgs, stats = ops.render_gaussians_batched(cat[0], cat[1], cat[2], dep, rad, torch.stack(masks).reshape(3, -1), vs, rs)
+    imgs.retain_grad()
+    out = ops.fused_l1_ssim_batched(imgs, strips, rows4)
+    coef = torch.tensor([1 - lam, -lam, 1 - lam, -lam, 0.0, 0.0], device="cuda")
+    (torch.dot(out.reshape(-1), coef) + 2 * lam).backward()
+    assert stats.shape == (3, 3) and int(stats[2].sum()) == 0 and int(stats[0, 2]) > 0
+    for k in range(3):
+        assert torch.equal(imgs[k], ref_img[k]), f"image of view {k}"
+        if ref_terms[k] is None:
+            assert float(out[k].abs().sum()) == 0.0 and float(imgs.grad[k].abs().sum()) == 0.0
+            assert float(imgs[k].abs().sum()) == 0.0        # no local tile: all zeros
+            for q in range(3):
+                assert float(L[k][0][q].grad.abs().sum()) == 0.0
+            continue
+        assert abs(float(out[k, 0]) - ref_terms[k][0]) <= 1e-6 * abs(ref_terms[k][0])
+        assert abs(float(out[k, 1]) - ref_terms[k][1]) <= 1e-6 * abs(ref_terms[k][1])
+        assert torch.equal(imgs.grad[k], ref_dimg[k]), f"dL/dimage of view {k}"
+        for q, name in enumerate(("means2D", "conic_opacity", "rgb")):
+            _grad_close(L[k][0][q].grad, ref_grads[k][q], f"view {k} dL/d{name}")
+    print("[parity] batched render + loss == per-camera calls (3 views, ragged, one without local tiles)")
+
+
+def test_trainer_batched_render_equals_per_camera_loop():
+    """Trainer.step with the batched render/loss path against the per-camera loop: same loss, same parameter gradients."""
+    from gs_b200 import pipeline
+    W, H, n, B = 320, 208, 25000, 3
+    sc = syn.make_scene(n, W, H, seed=77, radius_px=8.0)
+    cams = syn.make_batch_cameras(W, H, B)
+    gts = [torch.from_numpy(syn.make_gt_image(W, H, seed=80 + k)).pin_memory() for k in range(B)]
+    res = []
+    for batched in (False, True):
+        tr = pipeline.Trainer(sc, cams, gts, torch.device("cuda"), batched_render=batched)
+        loss = tr.step(resident=False)
+        res.append((loss, [t.grad.clone() for t in tr.params.raw_parameters()], tr.means2D.grad.clone(), tr.io_bytes_per_step()))
+    assert abs(res[0][0] - res[1][0]) <= 2e-6 * abs(res[0][0])
+    for a, b, name in zip(res[1][1], res[0][1], ("xyz", "f_dc", "f_rest", "scaling", "rotation", "opacity")):
+        _grad_close(a, b, name)
+    _grad_close(res[1][2], res[0][2], "means2D.grad (densification statistic)")
+    assert res[0][3][0] == res[1][3][0] and res[1][3][1] < res[0][3][1]   # same GT bytes in, one count read back, not B
+
+
 def test_full_size_properties_config_c2():
     """BASELINE.json configs[1] at full size (2 M Gaussians, 1920x1080): too big for the oracle in a test, so the
     CUDA path is checked through size-independent properties -- sortedness and bookkeeping of the binning, bit-exact
