@@ -335,6 +335,8 @@ def run_ours(args):
             "roofline": roofline, "clocks": clocks}
     if phase_ms is not None:  # multi-GPU only; measured outside the timed regions (see above)
         line["phase_ms_serialised"] = phase_ms
+        line["config"]["exchange"] = ("NVLink peer-memory stores fused into the pack kernels (gs_xchg_pack_p2p)"
+                                      if trainer._peer is not None else "NCCL all_to_all_single")
     if not args.no_cpu_baseline:
         r = cpu_arm(cfg, args.cpu_sample, 1, 1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

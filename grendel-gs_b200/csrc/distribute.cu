@@ -4,6 +4,8 @@
 //   gs_mask_scan/pack/unpack       replace the per-(destination, camera) nonzero() + index_select + cat
 //                                  glue of gaussian_renderer/__init__.py:590-607,651-658
 // Pure integer / byte work, HBM bound: 12 B read and world_size bytes written per splat.
+#include <cstring>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -424,6 +426,195 @@ extern "C" int gs_xchg_scatter_grad(int B, int P, int W, const uint8_t *flags, c
     GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
     dim3 grid((P + DT_THREADS - 1) / DT_THREADS, B);
     k_xchg_scatter_grad<<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(B, P, W, flags, gpos, grad_rows, d);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+// ---- exchange over NVLink peer memory: pack + transfer in ONE kernel ---------------------------------------------
+// all_to_all_single moves a rank's rows through NCCL's point-to-point channels: two device copies (pack into the send
+// buffer, NCCL from there into the peer's receive buffer) and a few channels per peer pair -- measured 0.40 / 0.53 ms
+// for the 37 / 31 MB a rank exchanges at W = 2 (profiles/), ten times the NVLink wire time.  Here every rank's receive
+// buffer is a cudaMalloc allocation exported through CUDA IPC and mapped by all peers, and the pack kernel stores each
+// row straight into ITS FINAL ROW of the destination's buffer:
+//     row in rank j's buffer = recv_base_j[me] + (gpos - send_base_me[j])        (both bases follow from the counts)
+// A warp compacts the rows it owns for one destination in shared memory and writes them with coalesced 128-byte
+// stores, which is what NVLink wants.  The same kernel serves the local part (destination == me).  The backward is the
+// mirror image: gradient rows go straight into the row of the SOURCE rank's buffer its scatter kernel reads.
+// Ordering: the host enqueues a 4-byte all-reduce after the kernel; it completes on a rank once every peer's kernel has
+// finished, so the consumer that follows it in stream order sees all rows.  Buffers are reused every step: a peer only
+// writes after it has received this rank's counts of the NEXT step, which this rank sends after its consumers ran.
+extern "C" int gs_peer_alloc(size_t bytes, void **dev_ptr, void *ipc_handle_64) {
+    GS_REQUIRE(bytes > 0 && dev_ptr && ipc_handle_64, "arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    GS_CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        gs_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return GS_ECUDA;
+    }
+    memcpy(ipc_handle_64, &h, 64);
+    *dev_ptr = p;
+    return GS_OK;
+}
+
+extern "C" int gs_peer_open(const void *ipc_handle_64, void **peer_ptr) {
+    GS_REQUIRE(ipc_handle_64 && peer_ptr, "arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle_64, 64);
+    GS_CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GS_OK;
+}
+
+extern "C" int gs_peer_close(void *peer_ptr) {
+    if (peer_ptr) GS_CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return GS_OK;
+}
+
+extern "C" int gs_peer_free(void *dev_ptr) {
+    if (dev_ptr) GS_CUDA_TRY(cudaFree(dev_ptr));
+    return GS_OK;
+}
+
+// The active lanes of a warp each own one row of NF floats destined for `dst` (rows of lanes with consecutive active
+// ranks are adjacent in memory when they go to the same buffer): compact them in shared memory, then store
+// element-wise with consecutive lanes on consecutive addresses.
+template <int NF>
+GS_D void warp_store_rows(bool active, float *dst, const float (&v)[NF], float *s_val, float **s_ptr, int lane) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, active);
+    if (mask == 0u) return;
+    const int q = __popc(mask & ((1u << lane) - 1u));
+    if (active) {
+#pragma unroll
+        for (int c = 0; c < NF; c++) s_val[q * NF + c] = v[c];
+        s_ptr[q] = dst;
+    }
+    __syncwarp();
+    const int n = __popc(mask) * NF;
+    for (int t = lane; t < n; t += 32) {
+        const int r = t / NF, c = t - r * NF;
+        s_ptr[r][c] = s_val[t];
+    }
+    __syncwarp();
+}
+
+struct XPeers { float *base[XW]; int32_t delta[XW]; };  // destination buffer of rank j and (its row) - (my send row)
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_xchg_pack_p2p(int B, int P, int Wr, XIn in, const uint8_t *__restrict__ flags, const int32_t *__restrict__ gpos,
+                XPeers peers) {
+    __shared__ float s_val[DT_THREADS / 32][32 * ROW_FLOATS];
+    __shared__ float *s_ptr[DT_THREADS / 32][32];
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool valid = i < P;
+    bool any = false;
+    if (valid)
+        for (int j = 0; j < Wr; j++) any |= flags[((size_t)j * B + k) * P + i] != 0;
+    float v[ROW_FLOATS];
+#pragma unroll
+    for (int c = 0; c < ROW_FLOATS; c++) v[c] = 0.f;
+    if (any) {
+        const float2 m = *reinterpret_cast<const float2 *>(in.m2[k] + 2 * i);
+        const float4 co = *reinterpret_cast<const float4 *>(in.co[k] + 4 * i);
+        v[0] = m.x; v[1] = m.y;
+        v[2] = in.rgb[k][3 * i]; v[3] = in.rgb[k][3 * i + 1]; v[4] = in.rgb[k][3 * i + 2];
+        v[5] = co.x; v[6] = co.y; v[7] = co.z; v[8] = co.w;
+        v[9] = (float)in.rad[k][i]; v[10] = in.dep[k][i];
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+    for (int j = 0; j < Wr; j++) {
+        const size_t e = ((size_t)j * B + k) * P + (valid ? i : 0);
+        const bool hit = any && flags[e] != 0;
+        float *dst = hit ? peers.base[j] + ((size_t)gpos[e] + peers.delta[j]) * ROW_FLOATS : nullptr;
+        warp_store_rows<ROW_FLOATS>(hit, dst, v, s_val[warp], s_ptr[warp], lane);
+    }
+    __threadfence_system();
+}
+
+// dst_rows_ptrs_host[j]: rank j's receive buffer as mapped into this process (this rank's own buffer for j == me);
+// row_delta_host[j] = recv_base_j[me] - send_base_me[j].
+extern "C" int gs_xchg_pack_p2p(int B, int P, int W, const uint8_t *flags, const int32_t *gpos,
+                                const void *const *means2D_ptrs_host, const void *const *rgb_ptrs_host,
+                                const void *const *conic_opacity_ptrs_host, const void *const *radii_ptrs_host,
+                                const void *const *depths_ptrs_host, void *const *dst_rows_ptrs_host,
+                                const int32_t *row_delta_host, void *stream) {
+    GS_REQUIRE(B > 0 && B <= XB && W > 0 && W <= XW && P >= 0, "sizes");
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(flags && gpos && means2D_ptrs_host && rgb_ptrs_host && conic_opacity_ptrs_host && radii_ptrs_host &&
+                   depths_ptrs_host && dst_rows_ptrs_host && row_delta_host, "null pointer");
+    XIn in;
+    fill_in(in, B, means2D_ptrs_host, rgb_ptrs_host, conic_opacity_ptrs_host, radii_ptrs_host, depths_ptrs_host);
+    XPeers peers;
+    for (int j = 0; j < XW; j++) {
+        peers.base[j] = j < W ? (float *)dst_rows_ptrs_host[j] : nullptr;
+        peers.delta[j] = j < W ? row_delta_host[j] : 0;
+        GS_REQUIRE(j >= W || peers.base[j] != nullptr, "null destination buffer");
+    }
+    GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
+    dim3 grid((P + DT_THREADS - 1) / DT_THREADS, B);
+    k_xchg_pack_p2p<<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(B, P, W, in, flags, gpos, peers);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+struct XSegPeers { float *base[XSEG]; };  // per recv segment: first gradient row of that block in the SOURCE's buffer
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_xchg_pack_grad_p2p(int total, XSegs segs, XIn g, XSegPeers dst) {
+    __shared__ float s_val[DT_THREADS / 32][32 * GRAD_FLOATS];
+    __shared__ float *s_ptr[DT_THREADS / 32][32];
+    const int r = blockIdx.x * DT_THREADS + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool valid = r < total;
+    float v[GRAD_FLOATS];
+#pragma unroll
+    for (int t = 0; t < GRAD_FLOATS; t++) v[t] = 0.f;
+    float *out = nullptr;
+    if (valid) {
+        const int s = xseg_find(segs, r);
+        const int k = segs.cam[s], off = r - segs.recv_start[s], i = segs.dst_start[s] + off;
+        if (g.m2[k]) { v[0] = g.m2[k][2 * i]; v[1] = g.m2[k][2 * i + 1]; }
+        if (g.rgb[k]) { v[2] = g.rgb[k][3 * i]; v[3] = g.rgb[k][3 * i + 1]; v[4] = g.rgb[k][3 * i + 2]; }
+        if (g.co[k]) {
+            const float4 c = *reinterpret_cast<const float4 *>(g.co[k] + 4 * i);
+            v[5] = c.x; v[6] = c.y; v[7] = c.z; v[8] = c.w;
+        }
+        out = dst.base[s] + (size_t)off * GRAD_FLOATS;
+    }
+    warp_store_rows<GRAD_FLOATS>(valid, out, v, s_val[warp], s_ptr[warp], lane);
+    __threadfence_system();
+}
+
+// seg_dst_ptrs_host[q]: address (in this process) of the FIRST gradient row of segment q inside the source rank's
+// gradient buffer, i.e. base_of_rank_i + (row where rank i packed its (camera k -> me) block) * 9 floats.  Segments as
+// in gs_xchg_unpack; only the non-empty ones are used.
+extern "C" int gs_xchg_pack_grad_p2p(int nseg, const int32_t *seg_recv_start_host, const int32_t *seg_len_host,
+                                     const int32_t *seg_cam_host, const int32_t *seg_dst_start_host, int total_rows,
+                                     int B, const void *const *d_means2D_ptrs_host, const void *const *d_rgb_ptrs_host,
+                                     const void *const *d_conic_opacity_ptrs_host, void *const *seg_dst_ptrs_host,
+                                     void *stream) {
+    GS_REQUIRE(B > 0 && B <= XB && total_rows >= 0, "sizes");
+    if (total_rows == 0) return GS_OK;
+    GS_REQUIRE(seg_dst_ptrs_host && d_means2D_ptrs_host && d_rgb_ptrs_host && d_conic_opacity_ptrs_host, "null pointer");
+    XSegs s;
+    int rc = fill_segs(s, nseg, seg_recv_start_host, seg_len_host, seg_cam_host, seg_dst_start_host);
+    if (rc != GS_OK) return rc;
+    XSegPeers dst;
+    int n = 0;  // same compaction as fill_segs: empty segments are dropped
+    for (int q = 0; q < nseg; q++) {
+        if (seg_len_host[q] <= 0) continue;
+        GS_REQUIRE(seg_dst_ptrs_host[q] != nullptr, "null destination buffer");
+        dst.base[n++] = (float *)seg_dst_ptrs_host[q];
+    }
+    for (int q = n; q < XSEG; q++) dst.base[q] = nullptr;
+    XIn g;
+    fill_in(g, B, d_means2D_ptrs_host, d_rgb_ptrs_host, d_conic_opacity_ptrs_host, nullptr, nullptr);
+    GsStageTimer timer(GS_STAGE_UNPACK, (cudaStream_t)stream);
+    k_xchg_pack_grad_p2p<<<(total_rows + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, (cudaStream_t)stream>>>(total_rows,
+                                                                                                              s, g, dst);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

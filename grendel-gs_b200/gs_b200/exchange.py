@@ -124,6 +124,102 @@ def _slab_ptrs(t, B):
     return (C.c_void_p * B)(*[base + k * step for k in range(B)])
 
 
+class PeerBuffers:
+    """NVLink peer-memory exchange buffers (include/grendel_gs_b200.h, gs_peer_* / gs_xchg_*_p2p): every rank owns one
+    receive buffer of `cap_rows` 11-float rows and one gradient buffer of `cap_rows` 9-float rows, exported over CUDA
+    IPC and mapped by all peers of the node.  recv[j] / grad[j] are rank j's buffers as addresses valid in THIS process.
+    Collective: every rank of `group` must construct it at the same point (handles travel by all_gather)."""
+
+    def __init__(self, world, me, cap_rows, device, group=None):
+        self.world, self.me, self.cap_rows, self.group = world, me, int(cap_rows), group
+        self._owned, self._opened = [], []
+        self.token = torch.zeros((1,), dtype=torch.float32, device=device)
+        # every local step that can fail is followed by an agreement (all-reduce MIN), so that either all ranks go on
+        # or all ranks raise -- never a rank stuck alone in a collective
+        handles, err = [0] * 128, None
+        try:
+            for q, nbytes in enumerate((self.cap_rows * ROW * 4, self.cap_rows * GROW * 4)):
+                ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+                _lib.call("gs_peer_alloc", nbytes, C.byref(ptr), handle)
+                self._owned.append(ptr.value)
+                handles[64 * q:64 * q + 64] = list(handle)
+        except Exception as e:   # noqa: BLE001
+            err = e
+        self._agree(err, device, "allocate / export")
+        mine = torch.tensor(handles, dtype=torch.uint8, device=device)
+        allh = torch.empty((world * 128,), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().reshape(world, 128).tolist()
+        self.recv, self.grad = [0] * world, [0] * world
+        try:
+            for j in range(world):
+                for q, table in enumerate((self.recv, self.grad)):
+                    if j == me:
+                        table[j] = self._owned[q]
+                        continue
+                    h, p = (C.c_ubyte * 64)(*allh[j][64 * q:64 * q + 64]), C.c_void_p()
+                    _lib.call("gs_peer_open", h, C.byref(p))
+                    self._opened.append(p.value)
+                    table[j] = p.value
+        except Exception as e:   # noqa: BLE001
+            err = e
+        self._agree(err, device, "map the peers' buffers")
+
+    def _agree(self, err, device, what):
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if float(ok.item()) < 1.0:
+            self.close()
+            raise RuntimeError(f"peer-memory exchange: could not {what} on every rank (this rank: {err!r})")
+
+    def barrier(self):
+        """Stream-ordered: completes on this rank once every rank's stream reached the same call (a 4-byte all-reduce;
+        the host does not block)."""
+        dist.all_reduce(self.token, op=dist.ReduceOp.MAX, group=self.group)   # MAX of zeros: the value never grows
+
+    def fits(self, cnt):
+        """Do all ranks' receive and send totals of this step fit the buffers?  Same answer on every rank."""
+        W, B = len(cnt), len(cnt[0])
+        worst = 0
+        for r in range(W):
+            worst = max(worst, sum(cnt[i][k][r] for i in range(W) for k in range(B)),
+                        sum(cnt[r][k][j] for k in range(B) for j in range(W)))
+        return worst <= self.cap_rows
+
+    def close(self):
+        for name, ptrs in (("gs_peer_close", self._opened), ("gs_peer_free", self._owned)):
+            for p in ptrs:
+                try:
+                    _lib.call(name, p)
+                except _lib.GsError:
+                    pass
+        self._opened, self._owned = [], []
+
+
+def peer_row_deltas(cnt, me):
+    """delta[j] = (first row of my block in rank j's receive buffer) - (first row of my block for j in my send order):
+    a row packed at position gpos of the send order lands in row gpos + delta[j] of rank j's buffer."""
+    W, B = len(cnt), len(cnt[0])
+    out, send_base = [], 0
+    for j in range(W):
+        recv_base = sum(cnt[i][k][j] for i in range(me) for k in range(B))
+        out.append(recv_base - send_base)
+        send_base += sum(cnt[me][k][j] for k in range(B))
+    return out
+
+
+def peer_grad_rows(cnt, me):
+    """For every (source rank i, camera k) segment of my receive buffer, in segments() order: the row of rank i's SEND
+    order where its (camera k -> me) block starts -- where my gradient rows for that block have to go."""
+    W, B = len(cnt), len(cnt[0])
+    rows = []
+    for i in range(W):
+        base = sum(cnt[i][k][j] for j in range(me) for k in range(B))
+        for k in range(B):
+            rows.append(base + sum(cnt[i][kk][me] for kk in range(k)))
+    return rows
+
+
 def _row_ptrs(t, starts, B):
     """Device pointers of rows starts[k] (k < B) of a contiguous (N, ...) tensor; NULLs if t is None."""
     if t is None:
@@ -148,12 +244,24 @@ class _ExchangeSplats(torch.autograd.Function):
         radii, depths = state["radii"], state["depths"]
         dev = m2.device
         s = ops._stream()
-        send = torch.empty((max(layout.total_send, 1), ROW), dtype=torch.float32, device=dev)
-        _lib.call("gs_xchg_pack", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), _slab_ptrs(m2, B),
-                  _slab_ptrs(rgb, B), _slab_ptrs(co, B), _slab_ptrs(radii, B), _slab_ptrs(depths, B), send.data_ptr(), s)
-        _t("x3 pack")
-        recv = torch.empty((max(layout.total_recv, 1), ROW), dtype=torch.float32, device=dev)
-        all_to_all_single(recv[:layout.total_recv], send[:layout.total_send], layout.recv_splits, layout.send_splits, group)
+        peer = state["peer"]
+        if peer is not None:
+            # pack + transfer in one kernel: rows go straight into their final rows of the destinations' buffers
+            _lib.call("gs_xchg_pack_p2p", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), _slab_ptrs(m2, B),
+                      _slab_ptrs(rgb, B), _slab_ptrs(co, B), _slab_ptrs(radii, B), _slab_ptrs(depths, B),
+                      (C.c_void_p * W)(*peer.recv), _i32(peer_row_deltas(state["cnt"], state["me"])), s)
+            _t("x3 pack")
+            peer.barrier()
+            recv_ptr = peer.recv[state["me"]]
+        else:
+            send = torch.empty((max(layout.total_send, 1), ROW), dtype=torch.float32, device=dev)
+            _lib.call("gs_xchg_pack", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), _slab_ptrs(m2, B),
+                      _slab_ptrs(rgb, B), _slab_ptrs(co, B), _slab_ptrs(radii, B), _slab_ptrs(depths, B), send.data_ptr(), s)
+            _t("x3 pack")
+            recv = torch.empty((max(layout.total_recv, 1), ROW), dtype=torch.float32, device=dev)
+            all_to_all_single(recv[:layout.total_recv], send[:layout.total_send], layout.recv_splits, layout.send_splits,
+                              group)
+            recv_ptr = recv.data_ptr()
         _t("x4 all_to_all")
         vs = state["view_start"]
         N = vs[B]
@@ -163,7 +271,7 @@ class _ExchangeSplats(torch.autograd.Function):
         orad = torch.empty((N,), dtype=torch.int32, device=dev)
         odep = torch.empty((N,), dtype=torch.float32, device=dev)
         rs, ln, cam, ds = state["segs"]
-        _lib.call("gs_xchg_unpack", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, recv.data_ptr(),
+        _lib.call("gs_xchg_unpack", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, recv_ptr,
                   B, _row_ptrs(om2, vs, B), _row_ptrs(orgb, vs, B), _row_ptrs(oco, vs, B), _row_ptrs(orad, vs, B),
                   _row_ptrs(odep, vs, B), s)
         ctx.state = state
@@ -180,28 +288,54 @@ class _ExchangeSplats(torch.autograd.Function):
         vs = state["view_start"]
         _t("b1 loss+render backward")
         g_m2, g_rgb, g_co = (None if t is None else t.contiguous() for t in (g_m2, g_rgb, g_co))
-        grecv = torch.empty((max(layout.total_recv, 1), GROW), dtype=torch.float32, device=dev)
         rs, ln, cam, ds = state["segs"]
-        _lib.call("gs_xchg_pack_grad", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, B,
-                  _row_ptrs(g_m2, vs, B), _row_ptrs(g_rgb, vs, B), _row_ptrs(g_co, vs, B), grecv.data_ptr(), s)
-        _t("b2 pack_grad")
-        gsend = torch.empty((max(layout.total_send, 1), GROW), dtype=torch.float32, device=dev)
-        all_to_all_single(gsend[:layout.total_send], grecv[:layout.total_recv], layout.send_splits, layout.recv_splits, group)
+        peer = state["peer"]
+        if peer is not None:
+            # gradient rows go straight into the rows of the SOURCE ranks' buffers that their scatter kernels read
+            rows = peer_grad_rows(state["cnt"], state["me"])
+            dst = (C.c_void_p * len(rs))(*[peer.grad[q // B] + rows[q] * GROW * 4 for q in range(len(rs))])
+            _lib.call("gs_xchg_pack_grad_p2p", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, B,
+                      _row_ptrs(g_m2, vs, B), _row_ptrs(g_rgb, vs, B), _row_ptrs(g_co, vs, B), dst, s)
+            _t("b2 pack_grad")
+            peer.barrier()
+            gsend_ptr = peer.grad[state["me"]]
+        else:
+            grecv = torch.empty((max(layout.total_recv, 1), GROW), dtype=torch.float32, device=dev)
+            _lib.call("gs_xchg_pack_grad", len(rs), _i32(rs), _i32(ln), _i32(cam), _i32(ds), layout.total_recv, B,
+                      _row_ptrs(g_m2, vs, B), _row_ptrs(g_rgb, vs, B), _row_ptrs(g_co, vs, B), grecv.data_ptr(), s)
+            _t("b2 pack_grad")
+            gsend = torch.empty((max(layout.total_send, 1), GROW), dtype=torch.float32, device=dev)
+            all_to_all_single(gsend[:layout.total_send], grecv[:layout.total_recv], layout.send_splits, layout.recv_splits,
+                              group)
+            gsend_ptr = gsend.data_ptr()
         _t("b3 all_to_all")
         d_m2 = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
         d_rgb = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
         d_co = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
-        _lib.call("gs_xchg_scatter_grad", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), gsend.data_ptr(),
+        _lib.call("gs_xchg_scatter_grad", B, P, W, state["flags"].data_ptr(), state["gpos"].data_ptr(), gsend_ptr,
                   _slab_ptrs(d_m2, B), _slab_ptrs(d_rgb, B), _slab_ptrs(d_co, B), s)
         return None, d_m2, d_rgb, d_co
 
 
-def exchange(means2D, rgb, conic_opacity, radii, depths, strategies, settings, world, me, group=None):
+def open_peer_buffers(world, me, cap_rows, device, group=None):
+    """PeerBuffers if every rank of the group could allocate, export and map them, else None on ALL ranks (the
+    exchange then uses all_to_all_single).  Collective."""
+    if world <= 1 or dist.get_backend(group) != "nccl":
+        return None
+    try:
+        return PeerBuffers(world, me, cap_rows, device, group)   # raises on every rank or on none
+    except RuntimeError as e:   # IPC not permitted in this container, out of memory, no peer access ...
+        import warnings
+        warnings.warn(f"rank {me}: NVLink peer-memory exchange unavailable ({e}); using all_to_all_single")
+        return None
+
+
+def exchange(means2D, rgb, conic_opacity, radii, depths, strategies, settings, world, me, group=None, peer=None):
     """Per-camera view of exchange_cat (the reference's return shape, gaussian_renderer/__init__.py:1010-1023):
     a list of B tuples (means2D, rgb, conic_opacity, radii, depths) -- row slices of the concatenated tensors, empty
     where this rank renders no strip of the camera -- and the all-gathered counts."""
     (m2, c3, co, rad, dep), view_start, cnt = exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies,
-                                                           settings, world, me, group)
+                                                           settings, world, me, group, peer)
     out = []
     for k in range(len(view_start) - 1):
         a, b = view_start[k], view_start[k + 1]
@@ -209,9 +343,11 @@ def exchange(means2D, rgb, conic_opacity, radii, depths, strategies, settings, w
     return out, cnt
 
 
-def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, settings, world, me, group=None):
+def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, settings, world, me, group=None, peer=None):
     """means2D (B,P,2), rgb (B,P,3), conic_opacity (B,P,4), radii (B,P) int32, depths (B,P): the local shard projected
     into the B cameras of the step (ops.preprocess_gaussians_batched, or torch.stack of per-camera results).
+    peer: PeerBuffers -> rows travel by direct NVLink stores from the pack kernels (steps whose totals exceed the
+    buffers, and peer=None, go through all_to_all_single).
     Returns ((means2D (N,2), rgb (N,3), conic_opacity (N,4), radii (N), depths (N)), view_start, cnt): the splats this
     rank has to render, all cameras concatenated in camera order (camera k = rows [view_start[k], view_start[k+1]),
     none if the rank renders no strip of it), and the all-gathered counts cnt[i][k][j] (the reference's
@@ -241,7 +377,8 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
     view_start = [0]
     for n in layout.n_recv:
         view_start.append(view_start[-1] + n)
+    use_peer = peer is not None and peer.fits(cnt)   # decided from the all-gathered counts: identical on all ranks
     state = dict(layout=layout, group=group, radii=radii, depths=depths, flags=flags, gpos=gpos, B=B, P=P, W=world,
-                 segs=segments(layout), view_start=view_start)
+                 segs=segments(layout), view_start=view_start, peer=peer if use_peer else None, cnt=cnt, me=me)
     res = _ExchangeSplats.apply(state, means2D, rgb, conic_opacity)
     return res, view_start, cnt

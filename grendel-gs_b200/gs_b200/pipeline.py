@@ -113,9 +113,20 @@ class Trainer:
     """
 
     def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None,
-                 fused_activations=True, border_exchange=False, batched_render=True):
+                 fused_activations=True, border_exchange=False, batched_render=True, peer_exchange=None,
+                 peer_cap_rows=None):
         from . import exchange as _ex
         self._ex = _ex
+        # splat / gradient rows travel by direct NVLink stores from the pack kernels (exchange.PeerBuffers) instead of
+        # all_to_all_single; peer_exchange=None: on unless GS_B200_EXCHANGE=nccl.  Buffers hold peer_cap_rows rows
+        # (default 1.25 x the scene's Gaussians); a step that needs more falls back to all_to_all_single.
+        if peer_exchange is None:
+            import os as _os
+            peer_exchange = _os.environ.get("GS_B200_EXCHANGE", "p2p") != "nccl"
+        self._peer = None
+        if world > 1 and peer_exchange:
+            cap = int(peer_cap_rows) if peer_cap_rows else int(1.25 * scene["means3D"].shape[0]) + 65536
+            self._peer = _ex.open_peer_buffers(world, rank, cap, device, group)
         # bin + blend + loss of all B cameras in one pass (ops.render_gaussians_batched) instead of the reference's
         # per-camera loop (render_final, gaussian_renderer/__init__.py:1217-1288); False keeps the per-camera calls
         self.batched_render = batched_render
@@ -251,9 +262,10 @@ class Trainer:
         if self.world > 1:
             if use_batched:
                 cat, view_start, cnt = self._ex.exchange_cat(*batched, strategies, settings, self.world, self.rank,
-                                                             self.group)
+                                                             self.group, self._peer)
             else:
-                redistributed, cnt = self._ex.exchange(*batched, strategies, settings, self.world, self.rank, self.group)
+                redistributed, cnt = self._ex.exchange(*batched, strategies, settings, self.world, self.rank, self.group,
+                                                       self._peer)
         elif use_batched:   # (B,P,.) stacked IS the concatenation: camera k = rows [k P, (k+1) P)
             Pn = batched[0].shape[1]
             cat = (batched[0].reshape(-1, 2), batched[1].reshape(-1, 3), batched[2].reshape(-1, 4),

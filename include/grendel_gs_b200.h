@@ -310,6 +310,33 @@ GS_API int gs_xchg_scatter_grad(int B, int P, int W, const uint8_t *flags, const
                                 void *const *d_means2D_ptrs_host, void *const *d_rgb_ptrs_host,
                                 void *const *d_conic_opacity_ptrs_host, void *stream);
 
+/* ---- the same exchange over NVLink peer memory: pack + transfer fused in one kernel -----------------------------
+ * Replaces torch.distributed.all_to_all_single (gaussian_renderer/__init__.py:609-628 forward, its autograd mirror
+ * backward) for ranks of one NVLink/NVSwitch node.  Each rank owns one receive buffer (11-float rows) and one
+ * gradient buffer (9-float rows), allocated by gs_peer_alloc and exported as a 64-byte CUDA IPC handle; peers map
+ * them with gs_peer_open.  gs_xchg_pack_p2p stores every row directly into its final row of the destination's
+ * receive buffer (the row all_to_all_single would have delivered it to), gs_xchg_pack_grad_p2p stores every gradient
+ * row directly into the row of the source's gradient buffer that gs_xchg_scatter_grad reads.  The caller orders
+ * producers and consumers across ranks (a 4-byte all-reduce enqueued after the kernel; see csrc/distribute.cu). */
+GS_API int gs_peer_alloc(size_t bytes, void **dev_ptr, void *ipc_handle_64);
+GS_API int gs_peer_open(const void *ipc_handle_64, void **peer_ptr);
+GS_API int gs_peer_close(void *peer_ptr);
+GS_API int gs_peer_free(void *dev_ptr);
+/* dst_rows_ptrs_host: HOST array of W pointers, rank j's receive buffer as mapped in this process (own buffer for
+ * j == me); row_delta_host: HOST (W) = recv_base_j[me] - send_base_me[j]. */
+GS_API int gs_xchg_pack_p2p(int B, int P, int W, const uint8_t *flags, const int32_t *gpos,
+                            const void *const *means2D_ptrs_host, const void *const *rgb_ptrs_host,
+                            const void *const *conic_opacity_ptrs_host, const void *const *radii_ptrs_host,
+                            const void *const *depths_ptrs_host, void *const *dst_rows_ptrs_host,
+                            const int32_t *row_delta_host, void *stream);
+/* seg_dst_ptrs_host: HOST array of nseg pointers, the first gradient row of segment q inside the SOURCE rank's
+ * gradient buffer (as mapped in this process). */
+GS_API int gs_xchg_pack_grad_p2p(int nseg, const int32_t *seg_recv_start_host, const int32_t *seg_len_host,
+                                 const int32_t *seg_cam_host, const int32_t *seg_dst_start_host, int total_rows, int B,
+                                 const void *const *d_means2D_ptrs_host, const void *const *d_rgb_ptrs_host,
+                                 const void *const *d_conic_opacity_ptrs_host, void *const *seg_dst_ptrs_host,
+                                 void *stream);
+
 /* ---- sparse per-Gaussian gradient all-reduce staging (replicated Gaussians) ----------------------------------
  * /root/reference/scene/gaussian_model.py:1332-1391 (get_sparse_ids, sync_gradients_sparsely) and the
  * "fused_sparse" mode it leaves NotImplemented (:1438-1439).  mask[i] = _xyz.grad row i is non-zero; after an

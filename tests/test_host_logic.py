@@ -208,3 +208,26 @@ def test_layout_is_consistent_without_a_group():
             assert off == pos or n == 0
             pos = max(pos, off + n)
         assert pos == lays[a].total_send
+    # peer-memory exchange addressing: a row packed at send position g for destination j lands in row g + delta[j] of
+    # rank j's receive buffer -- exactly where all_to_all_single would have delivered it -- and its gradient goes back
+    # to row g of the source's gradient buffer
+    for me in range(W):
+        delta = exchange.peer_row_deltas(cnt, me)
+        for k in range(B):
+            for c, j in enumerate(gpu_ids[k]):
+                if cnt[me][k][j]:
+                    assert lays[me].dst_off[k][c] + delta[j] == lays[j].seg_off[k][me]
+        grows = exchange.peer_grad_rows(cnt, me)
+        rs, ln, cam, ds = exchange.segments(lays[me])
+        assert len(grows) == len(rs) == W * B
+        for q in range(W * B):
+            i, k = q // B, q % B
+            assert cam[q] == k
+            if ln[q]:
+                assert grows[q] == lays[i].dst_off[k][gpu_ids[k].index(me)]
+    fits = exchange.PeerBuffers.fits
+    total = max(max(l.total_recv, l.total_send) for l in lays)
+    holder = type("H", (), {"cap_rows": total})()
+    assert fits(holder, cnt)
+    holder.cap_rows = total - 1
+    assert not fits(holder, cnt)
