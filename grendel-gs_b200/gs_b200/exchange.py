@@ -14,6 +14,7 @@ receiver, sources in rank order.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -38,23 +39,31 @@ class Layout:
     """
 
     def __init__(self, cnt, me, gpu_ids_per_cam):
-        W, B = len(cnt), len(cnt[0])
+        # runs on the critical path right after the step's host sync (the GPU is idle until the pack kernel is
+        # launched): numpy prefix sums instead of O(W B^2) Python loops
+        c = np.asarray(cnt, dtype=np.int64).reshape(len(cnt), len(cnt[0]), len(cnt))     # (W, B, W)
+        W, B = c.shape[0], c.shape[1]
         self.W, self.B, self.me = W, B, me
-        self.send_splits = [sum(cnt[me][k][j] for k in range(B)) for j in range(W)]
-        self.recv_splits = [sum(cnt[i][k][me] for k in range(B)) for i in range(W)]
-        send_base = [sum(self.send_splits[:j]) for j in range(W)]
-        recv_base = [sum(self.recv_splits[:i]) for i in range(W)]
+        S = c.sum(axis=1)                                    # S[i][j]: rows rank i sends to rank j
+        send_base, recv_base = _excl(S[me]), _excl(S[:, me])
+        self.send_splits, self.recv_splits = S[me].tolist(), S[:, me].tolist()
         # camera k, local column c (destination gpu_ids[k][c]) -> first row in the send buffer
-        self.dst_off = []
-        for k in range(B):
-            self.dst_off.append([send_base[j] + sum(cnt[me][kk][j] for kk in range(k)) for j in gpu_ids_per_cam[k]])
+        before_send = _excl(c[me], axis=0)                   # [k][j]: rows of cameras < k that go to j
+        off = (send_base[None, :] + before_send).tolist()
+        self.dst_off = [[off[k][j] for j in gpu_ids_per_cam[k]] for k in range(B)]
         # camera k -> (segment offsets, segment lengths) in the recv buffer, one segment per source rank
-        self.seg_off, self.seg_len = [], []
-        for k in range(B):
-            self.seg_off.append([recv_base[i] + sum(cnt[i][kk][me] for kk in range(k)) for i in range(W)])
-            self.seg_len.append([cnt[i][k][me] for i in range(W)])
-        self.n_recv = [sum(l) for l in self.seg_len]
-        self.total_send, self.total_recv = sum(self.send_splits), sum(self.recv_splits)
+        mine = c[:, :, me]                                   # [i][k]: rows rank i sends me for camera k
+        self.seg_off = (recv_base[:, None] + _excl(mine, axis=1)).T.tolist()
+        self.seg_len = mine.T.tolist()
+        self.n_recv = mine.sum(axis=0).tolist()
+        self.seg_dst = _excl(mine, axis=0).T.tolist()        # [k][i]: first row of the segment inside camera k's output
+        self.total_send, self.total_recv = int(S[me].sum()), int(S[:, me].sum())
+
+
+def _excl(a, axis=0):
+    """Exclusive prefix sum along `axis`."""
+    out = np.cumsum(a, axis=axis)
+    return out - a
 
 
 def all_to_all_single(out, inp, out_splits, in_splits, group=None):
@@ -85,12 +94,12 @@ def all_to_all_single(out, inp, out_splits, in_splits, group=None):
 
 
 def gather_counts(local_counts, group=None):
-    """(B, W) int32 device tensor -> nested list cnt[i][k][j]; the step's one host sync."""
+    """(B, W) int32 device tensor -> (W, B, W) integer array cnt[i][k][j]; the step's one host sync."""
     W = dist.get_world_size(group)
     flat = local_counts.contiguous().reshape(-1)
     allc = torch.empty((W * flat.numel(),), dtype=flat.dtype, device=flat.device)
     dist.all_gather_into_tensor(allc, flat, group=group)
-    return allc.reshape((W,) + tuple(local_counts.shape)).cpu().tolist()
+    return allc.reshape((W,) + tuple(local_counts.shape)).cpu().numpy()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -113,7 +122,7 @@ def segments(layout):
             rs.append(layout.seg_off[k][i])
             ln.append(layout.seg_len[k][i])
             cam.append(k)
-            ds.append(sum(layout.seg_len[k][:i]))
+            ds.append(layout.seg_dst[k][i])
     return rs, ln, cam, ds
 
 
@@ -179,12 +188,8 @@ class PeerBuffers:
 
     def fits(self, cnt):
         """Do all ranks' receive and send totals of this step fit the buffers?  Same answer on every rank."""
-        W, B = len(cnt), len(cnt[0])
-        worst = 0
-        for r in range(W):
-            worst = max(worst, sum(cnt[i][k][r] for i in range(W) for k in range(B)),
-                        sum(cnt[r][k][j] for k in range(B) for j in range(W)))
-        return worst <= self.cap_rows
+        S = np.asarray(cnt, dtype=np.int64).sum(axis=1)     # S[i][j]: rows i -> j
+        return int(max(S.sum(axis=0).max(), S.sum(axis=1).max())) <= self.cap_rows
 
     def close(self):
         for name, ptrs in (("gs_peer_close", self._opened), ("gs_peer_free", self._owned)):
@@ -199,25 +204,17 @@ class PeerBuffers:
 def peer_row_deltas(cnt, me):
     """delta[j] = (first row of my block in rank j's receive buffer) - (first row of my block for j in my send order):
     a row packed at position gpos of the send order lands in row gpos + delta[j] of rank j's buffer."""
-    W, B = len(cnt), len(cnt[0])
-    out, send_base = [], 0
-    for j in range(W):
-        recv_base = sum(cnt[i][k][j] for i in range(me) for k in range(B))
-        out.append(recv_base - send_base)
-        send_base += sum(cnt[me][k][j] for k in range(B))
-    return out
+    S = np.asarray(cnt, dtype=np.int64).sum(axis=1)         # S[i][j]: rows i -> j
+    recv_base = S[:me].sum(axis=0)                          # [j]: rows of ranks < me in rank j's buffer
+    return (recv_base - _excl(S[me])).tolist()
 
 
 def peer_grad_rows(cnt, me):
     """For every (source rank i, camera k) segment of my receive buffer, in segments() order: the row of rank i's SEND
     order where its (camera k -> me) block starts -- where my gradient rows for that block have to go."""
-    W, B = len(cnt), len(cnt[0])
-    rows = []
-    for i in range(W):
-        base = sum(cnt[i][k][j] for j in range(me) for k in range(B))
-        for k in range(B):
-            rows.append(base + sum(cnt[i][kk][me] for kk in range(k)))
-    return rows
+    c = np.asarray(cnt, dtype=np.int64)
+    base = c[:, :, :me].sum(axis=(1, 2))                    # [i]: rows rank i sends to ranks < me
+    return (base[:, None] + _excl(c[:, :, me], axis=1)).reshape(-1).tolist()
 
 
 def _row_ptrs(t, starts, B):
