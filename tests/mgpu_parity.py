@@ -26,6 +26,7 @@ from gs_b200 import division, ops, pipeline, synthetic as syn  # noqa: E402
 
 
 def main():
+    sys.stdout.reconfigure(line_buffering=True)   # progress survives a timeout kill when stdout is a pipe
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -93,7 +94,8 @@ def main():
 
     if rank == 0:
         from oracle.oracle import Oracle
-        o = Oracle(np.float32)
+        # the other ranks wait in the next collective; torchrun's OMP_NUM_THREADS=1 default does not bind the oracle
+        o = Oracle(np.float32, threads=max(1, min(32, (os.cpu_count() or 8) // 2)))
         T = tr.tile_y * tr.tile_x
         exp = {n: 0 for n in ("means3D", "scales", "rotations", "opacities", "shs")}
         tot_loss = 0.0
