@@ -349,6 +349,19 @@ GS_API int gs_sparse_grad_pack(int P, const uint8_t *mask, const int32_t *pos, v
 GS_API int gs_sparse_grad_unpack(int P, const uint8_t *mask, const int32_t *pos, const float *rows,
                                  void *const *grads_host, void *stream);
 
+/* ---- fused Adam step -- /root/reference/train_internal.py:316-329 ---------------------------
+ * torch.optim.Adam(l, lr=0.0, eps=1e-15) over the six parameter groups (scene/gaussian_model.py:257-292), preceded by
+ * `param.grad /= args.bsz` (train_internal.py:319-324): one launch for up to GS_ADAM_MAX_TENSORS tensors with
+ * per-tensor lr / betas / eps, torch's arithmetic and operation order (no weight decay, no amsgrad).
+ * All *_host are HOST arrays of num_tensors entries; pointers are fp32 contiguous device tensors of numel[k] elements
+ * (NULL grad: tensor skipped, like .grad is None).  step[k] >= 1: the step counter AFTER this update.
+ * grad_scale multiplies every gradient first (1/bsz).  params, exp_avg, exp_avg_sq are updated in place. */
+#define GS_ADAM_MAX_TENSORS 8
+GS_API int gs_adam_step(int num_tensors, const int64_t *numel_host, void *const *params_host,
+                        const void *const *grads_host, void *const *exp_avg_host, void *const *exp_avg_sq_host,
+                        const double *lr_host, const double *beta1_host, const double *beta2_host,
+                        const double *eps_host, const int64_t *step_host, float grad_scale, void *stream);
+
 /* ---- legacy tile-mask / tile-exchange helpers (dead code in the shipped trainer) ------
  * _C.get_touched_locally                     -- gaussian_renderer/loss_distribution.py:136-141
  * _C.get_pixels_compute_locally_and_in_rect  -- loss_distribution.py:205-213
