@@ -199,6 +199,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    # A/B of experimental kernels (include/grendel_gs_b200.h, gs_debug_set): GS_B200_DEBUG_FLAGS=2 python bench.py;
+    # a run with flags set is labelled in config.debug_flags and is NOT the shipped configuration
+    debug_flags = int(os.environ.get("GS_B200_DEBUG_FLAGS", "0"))
+    if debug_flags:
+        _lib.debug_set(debug_flags)
 
     cfg = workload(args)
     W, H, N = cfg["width"], cfg["height"], cfg["n"]
@@ -333,6 +338,8 @@ def run_ours(args):
             "library_calls": {"cub::DeviceScan": int(launches.get("30 InclusiveSum", 0)),
                               "cub::DeviceRadixSort": int(launches.get("50 SortPairs", 0))},
             "roofline": roofline, "clocks": clocks}
+    if debug_flags:
+        line["config"]["debug_flags"] = debug_flags
     if phase_ms is not None:  # multi-GPU only; measured outside the timed regions (see above)
         line["phase_ms_serialised"] = phase_ms
         line["config"]["exchange"] = ("NVLink peer-memory stores fused into the pack kernels (gs_xchg_pack_p2p)"

@@ -384,6 +384,216 @@ k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
     }
 }
 
+// ---- backward, EXPERIMENTAL variant (off by default; gs_debug_set(GS_DEBUG_BWD_WHT_64 / _128)) ---------------------
+// Same walk, same per-pixel arithmetic; only the lane -> warp reduction of the six moments differs.  SASS of
+// k_blend_bwd: 110 instructions per fully processed (warp, splat) pair, 51 of them forming and reducing the nine sums
+// (14 SHFL + 14 FSEL + 14 FADD + 9 FMUL).  Here the per-pixel weight m alone goes through a 5-stage Walsh-Hadamard
+// butterfly (5 SHFL + 5 FFMA): afterwards lane L holds W_L = sum_l m_l (-1)^popc(L & l).  A pixel's offset inside the
+// warp's 8x4 block is a polynomial of degree <= 2 in the lane bits (lx = b0 + 2 b1 + 4 b2, ly = b3 + 2 b4), so all six
+// moments about the block origin are linear combinations of the 16 coefficients with popc(L) <= 2:
+//     sum m b_i     = (W_0 - W_{e_i}) / 2          sum m b_i b_j = (W_0 - W_{e_i} - W_{e_j} + W_{e_i + e_j}) / 4
+// The 16 lanes that hold them store them (one STS), the flush thread of the splat forms the moments and shifts them to
+// the splat centre.  The three colour sums take a 4-value transposing butterfly (6 SHFL).  30 instructions instead of
+// 51, at the price of 19 instead of 9 floats of shared memory per (warp, entry) -- hence the CHUNK parameter: 64
+// entries keep 5 CTAs per SM, 128 entries halve the barriers but leave 2 CTAs per SM.  To be timed on the device.
+#define BWH_NVAL 19
+
+template <int CHUNK>
+__global__ void __launch_bounds__(BL_THREADS, CHUNK == 64 ? 5 : 2)   // 44 KB / 83 KB of shared memory per CTA
+k_blend_bwd_wht(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
+                const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
+                const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
+                const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
+                float *__restrict__ d_means2D, float *__restrict__ d_conic_opacity, float *__restrict__ d_rgb) {
+    constexpr int STRIDE = CHUNK + 1;
+    extern __shared__ float s_acc[];  // [BL_WARPS][BWH_NVAL][STRIDE]
+    __shared__ SRec s_rec[CHUNK];
+    __shared__ uint32_t s_id[CHUNK];
+    __shared__ uint8_t s_cull[CHUNK];
+    __shared__ uint32_t s_mask[BL_WARPS][CHUNK / 32];
+    __shared__ uint32_t s_max[BL_WARPS];
+    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
+    if (!compute_locally[blockIdx.x]) return;
+    const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int px, py;
+    pixel_of_thread(tile, gx, px, py);
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)py * W + px;
+    final_T += (size_t)view * HW;
+    n_contrib += (size_t)view * HW;
+    dL_dimage += (size_t)view * 3 * HW;
+    const uint2 range = ranges[blockIdx.x];
+    const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
+    const float pxf = (float)px, pyf = (float)py;
+    const float T_final = inside ? final_T[pix] : 0.f;
+    const uint32_t last = inside ? n_contrib[pix] : 0u;
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+    if (inside) { dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix]; }
+    const float bgdot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
+    const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
+    // where this lane's Walsh-Hadamard coefficient goes: 0 <- W_0, 1+i <- W_{e_i}, 6+pair(i,j) <- W_{e_i+e_j}
+    int slot = -1;
+    {
+        const int pc = __popc(lane);
+        if (pc == 0) slot = 0;
+        else if (pc == 1) slot = __ffs(lane);  // 1 + bit index
+        else if (pc == 2) {
+            const int i = __ffs(lane) - 1, j = 31 - __clz(lane);
+            slot = 6 + (i * (9 - i)) / 2 + (j - i - 1);
+        }
+    }
+    // sign of this lane in butterfly stage s: -1 if bit s of the lane is set
+    float sg[5];
+#pragma unroll
+    for (int s = 0; s < 5; s++) sg[s] = ((lane >> s) & 1) ? -1.f : 1.f;
+    const bool h16 = lane & 16, h8 = lane & 8;
+    uint32_t m = last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_max[warp] = m;
+    __syncthreads();
+    uint32_t n_total = 0;
+#pragma unroll
+    for (int w = 0; w < BL_WARPS; w++) n_total = max(n_total, s_max[w]);
+    const uint32_t wlast = m;
+    float *acc_w = s_acc + (size_t)warp * BWH_NVAL * STRIDE;
+    // shared-window addresses of this lane's two store rows, formed once (entry j adds 4 j bytes)
+    const uint32_t st_w = gs_smem_u32(acc_w + (slot >= 0 ? slot : 0) * STRIDE);
+    const uint32_t st_q = gs_smem_u32(acc_w + (16 + ((lane >> 3) & 3)) * STRIDE);
+    const bool has_w = slot >= 0, has_q = (lane & 7) == 0 && lane < 24;  // colour totals end in lanes 0, 8, 16
+    float T = T_final, B0 = 0.f, B1 = 0.f, B2 = 0.f;
+    const int n_chunks = ((int)n_total + CHUNK - 1) / CHUNK;
+    for (int c = n_chunks - 1; c >= 0; c--) {
+        const int base = c * CHUNK;
+        const int cnt = min(CHUNK, (int)n_total - base);
+        __syncthreads();  // previous chunk's flush has finished reading shared memory
+        if ((int)threadIdx.x < cnt) {
+            const uint32_t g = ids[range.x + base + threadIdx.x];
+            s_id[threadIdx.x] = g;
+            const float4 *r = rec + (size_t)3 * g;
+            const float4 a = __ldg(r), b = __ldg(r + 1), cc = __ldg(r + 2);
+            s_rec[threadIdx.x].a = a; s_rec[threadIdx.x].b = b; s_rec[threadIdx.x].c = cc;
+            s_cull[threadIdx.x] = (uint8_t)block_mask(a.x, a.y, cc.z, cc.w, X0, Y0);
+        }
+        uint32_t wmask = 0u;
+        __syncthreads();
+        if ((uint32_t)base < wlast) {
+            for (int g0 = (cnt - 1) & ~31; g0 >= 0; g0 -= 32) {
+                const int jj = g0 + 31 - lane;
+                uint32_t cand = __ballot_sync(0xffffffffu, jj < cnt && ((s_cull[jj] >> warp) & 1));
+                uint32_t mybits = 0u;
+                const int last_rel = (int)last - base;
+                while (cand) {
+                    const int b31 = 32 - __ffs(cand);
+                    const int j = g0 + b31;
+                    cand &= cand - 1u;
+                    const SRec *sr = &s_rec[j];
+                    const float4 a = sr->a, b = sr->b;
+                    const float dx = a.x - pxf, dy = a.y - pyf;
+                    const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
+                    bool ok = (j < last_rel) && power >= b.z;
+                    if (!__any_sync(0xffffffffu, ok)) continue;
+                    const float G = gs_exp_neg(power);
+                    const float alpha = fminf(ALPHA_MAX, b.y * G);
+                    ok = ok && power <= 0.f && alpha >= ALPHA_MIN;
+                    if (!__any_sync(0xffffffffu, ok)) continue;
+                    const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
+                    const float ae = ok ? alpha : 0.f;
+                    float inv;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - ae));
+                    T = T * inv;
+                    const float d0 = b.w - B0, d1 = gb.x - B1, d2 = gb.y - B2;
+                    const float dL_dalpha = (d0 * dp0 + d1 * dp1 + d2 * dp2) * T - (T_final * inv) * bgdot;
+                    float w = ok ? b.y * dL_dalpha * G : 0.f;   // per-pixel weight m = dL/dG * G
+                    const float dch = ae * T;
+                    B0 += ae * d0; B1 += ae * d1; B2 += ae * d2;
+                    // Walsh-Hadamard butterfly of m over the 32 lanes
+#pragma unroll
+                    for (int s = 0; s < 5; s++) w = __fmaf_rn(sg[s], w, __shfl_xor_sync(0xffffffffu, w, 1 << s));
+                    // colour sums: 4-value transposing butterfly of (c0, c1, c2, 0)
+                    const float c0 = dch * dp0, c1 = dch * dp1, c2 = dch * dp2;
+                    float r0 = (h16 ? c2 : c0) + __shfl_xor_sync(0xffffffffu, h16 ? c0 : c2, 16);
+                    float r1 = (h16 ? 0.f : c1) + __shfl_xor_sync(0xffffffffu, h16 ? c1 : 0.f, 16);
+                    float q = (h8 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, h8 ? r0 : r1, 8);
+                    q += __shfl_xor_sync(0xffffffffu, q, 4);
+                    q += __shfl_xor_sync(0xffffffffu, q, 2);
+                    q += __shfl_xor_sync(0xffffffffu, q, 1);
+                    if (has_w) asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_w + 4u * (uint32_t)j), "f"(w) : "memory");
+                    if (has_q) asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_q + 4u * (uint32_t)j), "f"(q) : "memory");
+                    mybits |= 1u << b31;
+                }
+                if (lane == (g0 >> 5)) wmask = mybits;
+            }
+        }
+        if (lane < CHUNK / 32) s_mask[warp][lane] = wmask;
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            const int j = threadIdx.x;
+            const float4 a = s_rec[j].a, b = s_rec[j].b;
+            float s[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) s[q] = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < BL_WARPS; w++) {
+                if ((s_mask[w][j >> 5] >> (j & 31)) & 1u) {
+                    any = true;
+                    const float *cw = s_acc + (size_t)w * BWH_NVAL * STRIDE + j;
+                    float cf[BWH_NVAL];
+#pragma unroll
+                    for (int q = 0; q < BWH_NVAL; q++) cf[q] = cw[q * STRIDE];
+                    // with sum m b_i = (W_0 - E_i)/2 and sum m b_i b_j = (W_0 - E_i - E_j + P_ij)/4 substituted into
+                    // lx = b0 + 2 b1 + 4 b2, ly = b3 + 2 b4 and collected per coefficient
+                    // (E_i = cf[1+i]; P_ij = cf[6 + i(9-i)/2 + j-i-1]: P01 6, P02 7, P03 8, P04 9, P12 10, P13 11, P14 12,
+                    //  P23 13, P24 14, P34 15):
+                    const float W0 = cf[0], E0 = cf[1], E1 = cf[2], E2 = cf[3], E3 = cf[4], E4 = cf[5];
+                    const float Lx = 3.5f * W0 - 0.5f * E0 - E1 - 2.f * E2;                         // sum m lx
+                    const float Ly = 1.5f * W0 - 0.5f * E3 - E4;                                    // sum m ly
+                    const float Lxx = 17.5f * W0 - 3.5f * E0 - 7.f * E1 - 14.f * E2 + cf[6] + 2.f * cf[7] + 4.f * cf[10];
+                    const float Lyy = 3.5f * W0 - 1.5f * E3 - 3.f * E4 + cf[15];
+                    const float Lxy = 0.25f * (21.f * W0 - 3.f * E0 - 6.f * E1 - 12.f * E2 - 7.f * E3 - 14.f * E4 + cf[8] +
+                                               2.f * cf[9] + 2.f * cf[11] + 4.f * cf[12] + 4.f * cf[13] + 8.f * cf[14]);
+                    // offsets of the splat centre from this warp's block origin: dx = ux - lx, dy = uy - ly
+                    const float ux = a.x - (X0 + (float)((w & 1) * 8)), uy = a.y - (Y0 + (float)((w >> 1) * 4));
+                    s[0] += ux * W0 - Lx;
+                    s[1] += uy * W0 - Ly;
+                    s[2] += ux * (ux * W0 - 2.f * Lx) + Lxx;
+                    s[3] += ux * (uy * W0 - Ly) - uy * Lx + Lxy;
+                    s[4] += uy * (uy * W0 - 2.f * Ly) + Lyy;
+                    s[5] += W0;
+                    s[6] += cf[16]; s[7] += cf[17]; s[8] += cf[18];
+                }
+            }
+            if (any) {
+                const uint32_t g = s_id[j];
+                atomicAdd(d_means2D + 2 * (size_t)g, (2.f * a.z * s[0] + a.w * s[1]) * ddelx_dx);
+                atomicAdd(d_means2D + 2 * (size_t)g + 1, (2.f * b.x * s[1] + a.w * s[0]) * ddely_dy);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g, -0.5f * s[2]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 1, -s[3]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 2, -0.5f * s[4]);
+                atomicAdd(d_conic_opacity + 4 * (size_t)g + 3, __fdividef(s[5], b.y));
+                atomicAdd(d_rgb + 3 * (size_t)g, s[6]);
+                atomicAdd(d_rgb + 3 * (size_t)g + 1, s[7]);
+                atomicAdd(d_rgb + 3 * (size_t)g + 2, s[8]);
+            }
+        }
+    }
+}
+
+template <int CHUNK>
+static int launch_bwd_wht(int grid, cudaStream_t stream, int W, int H, int T1, const float4 *rec, const float *bg,
+                          const uint8_t *cl, const uint2 *ranges, const uint32_t *ids, const float *final_T,
+                          const uint32_t *n_contrib, const float *dimg, float *d_m2, float *d_co, float *d_rgb) {
+    const size_t dyn = sizeof(float) * BL_WARPS * BWH_NVAL * (CHUNK + 1);
+    GS_CUDA_TRY(cudaFuncSetAttribute(k_blend_bwd_wht<CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    k_blend_bwd_wht<CHUNK><<<grid, BL_THREADS, dyn, stream>>>(W, H, T1, rec, bg, cl, ranges, ids, final_T, n_contrib, dimg,
+                                                              d_m2, d_co, d_rgb);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
 int gs_launch_blend_forward(int num_views, int64_t R, int H, int W, const float *rec, const float *bg,
                             const uint8_t *compute_locally, const uint32_t *ranges, const uint32_t *ids_sorted,
                             float *image, float *final_T, uint32_t *n_contrib, int64_t *stats, cudaStream_t stream) {
@@ -431,6 +641,16 @@ extern "C" int gs_render_backward_batched(int num_views, int P, int64_t R, int i
     GS_REQUIRE(rec && bg && compute_locally && ranges && ids_sorted && final_T && n_contrib && dL_dimage, "null input");
     const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     GsStageTimer timer(GS_STAGE_BLEND_BWD, stream);
+    if (g_gs_debug_flags & (GS_DEBUG_BWD_WHT_64 | GS_DEBUG_BWD_WHT_128)) {  // experimental reduction, see above
+        const float4 *r4 = reinterpret_cast<const float4 *>(rec);
+        const uint2 *rg = reinterpret_cast<const uint2 *>(ranges);
+        if (g_gs_debug_flags & GS_DEBUG_BWD_WHT_64)
+            return launch_bwd_wht<64>(gx * gy * num_views, stream, image_width, image_height, gx * gy, r4, bg,
+                                      compute_locally, rg, ids_sorted, final_T, n_contrib, dL_dimage, dL_dmeans2D,
+                                      dL_dconic_opacity, dL_drgb);
+        return launch_bwd_wht<128>(gx * gy * num_views, stream, image_width, image_height, gx * gy, r4, bg, compute_locally,
+                                   rg, ids_sorted, final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity, dL_drgb);
+    }
     k_blend_bwd<<<gx * gy * num_views, BL_THREADS, 0, stream>>>(
         image_width, image_height, gx * gy, reinterpret_cast<const float4 *>(rec), bg, compute_locally,
         reinterpret_cast<const uint2 *>(ranges), ids_sorted, final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity,

@@ -240,7 +240,15 @@ GS_API const char *gs_profile_stage_name(int stage);
  * reference (which tests alpha per pixel, cuda_rasterizer/forward.cu:513-519) would have blended.
  * GS_DEBUG_NO_BLOCK_CULL makes gs_render_count write infinite extents, so tests can check that the culled and
  * unculled kernels produce the same image and n_contrib.  Returns the previous flags. */
-enum { GS_DEBUG_NO_BLOCK_CULL = 1 };
+enum {
+    GS_DEBUG_NO_BLOCK_CULL = 1,
+    /* EXPERIMENTAL, off by default: gs_render_backward with the Walsh-Hadamard moment reduction (csrc/blend.cu,
+     * k_blend_bwd_wht), 64- or 128-entry chunks; same inputs and outputs.  Written after round 1's GPU budget was
+     * spent: to be validated (tests/test_gpu_parity.py, GS_B200_EXPERIMENTAL=1) and timed before it may become the
+     * default. */
+    GS_DEBUG_BWD_WHT_64 = 2,
+    GS_DEBUG_BWD_WHT_128 = 4
+};
 GS_API int gs_debug_set(int flags);
 
 /* ---- per-strip loss -- gaussian_renderer/loss_distribution.py:2536-2585 + utils/loss_utils.py:88-132 ----

@@ -151,6 +151,33 @@ def test_render_backward_parity(o32, n, W, H, rad, bg):
         assert (a[untouched] == 0).all()
 
 
+@pytest.mark.skipif(__import__("os").environ.get("GS_B200_EXPERIMENTAL") != "1",
+                    reason="experimental kernels (off by default): set GS_B200_EXPERIMENTAL=1 to validate them")
+@pytest.mark.parametrize("flag", ["DEBUG_BWD_WHT_64", "DEBUG_BWD_WHT_128"])
+@pytest.mark.parametrize("n,W,H,rad,bg", [(20000, 320, 200, 7.0, (0.0, 0.0, 0.0)), (3000, 96, 64, 16.0, (0.3, 0.1, 0.7)),
+                                          (30000, 200, 120, 9.0, (0.2, 0.5, 0.9))])
+def test_experimental_backward_wht_parity(o32, flag, n, W, H, rad, bg):
+    """k_blend_bwd_wht (Walsh-Hadamard moment reduction, gs_debug_set) against the oracle and the default kernel."""
+    from gs_b200 import _lib
+    ref, rf, f, cl = _render_case(o32, n, W, H, rad, bg)
+    g = np.random.default_rng(2).normal(size=(3, H, W)).astype(np.float32)
+    rb = o32.render_backward(H, W, ref["means2D"], ref["conic_opacity"], ref["rgb"], bg, rf, g)
+    base = gu.render_backward(f, gu.to_dev(g))
+    old = _lib.debug_set(getattr(_lib, flag))
+    try:
+        got = gu.render_backward(f, gu.to_dev(g))
+    finally:
+        _lib.debug_set(old)
+    for k in ("means2D", "conic_opacity", "rgb"):
+        a = gu.npy(got[k])
+        assert np.isfinite(a).all()
+        frac, _ = gu.rel_report(f"{flag}.{k}", a, rb[k])
+        assert frac <= 5 * OUTLIER_FRAC, k
+        frac2, _ = gu.rel_report(f"{flag}.vs_default.{k}", a, gu.npy(base[k]))
+        assert frac2 <= 5 * OUTLIER_FRAC, k
+        assert (a[~np.isin(np.arange(n), rf["ids"])] == 0).all()
+
+
 def test_whole_step_parity_config_c1(o32):
     """BASELINE.json configs[0]: 50k Gaussians, 400x400, forward + loss + backward, through the public operator."""
     import diff_gaussian_rasterization as dgr
