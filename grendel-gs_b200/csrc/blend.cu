@@ -594,6 +594,163 @@ static int launch_bwd_wht(int grid, cudaStream_t stream, int W, int H, int T1, c
     return GS_OK;
 }
 
+// ---- backward, EXPERIMENTAL variant 2 (off by default; gs_debug_set(GS_DEBUG_BWD_AUTO)) ---------------------------
+// "Warp-autonomous": no CTA barrier and no shared partial-sum slots at all.  Every warp walks the tile's list on its
+// own for its two 4x4 pixel blocks (one per half-warp, the forward's layout: ~60 % useful lanes instead of 37 %), 32
+// entries at a time: lane l loads entry l's record into a warp-private staging row and computes its block mask, two
+// ballots give each half-warp its candidates, and each candidate pair is reduced over the 16 lanes of its half (9-value
+// transposing butterfly, 12 SHFL for BOTH halves together) and leaves the SM at once as ONE predicated RED.ADD
+// instruction: the lane pair that ends up holding a sum adds "its" terms of the gradient (even lane / odd lane take
+// the two outputs a sum feeds -- e.g. sum(m dx) feeds dL/dmean_x with 2a' and dL/dmean_y with b').  That is 11 global
+// atomics per (4x4 block, splat) instead of 9 per (tile, splat), in exchange for: no flush pass, no barrier stalls (the
+// default kernel idles ~20 % of its issue slots waiting at 3 barriers per chunk), and ~75 instead of 110 issued
+// instructions per 8x4-block-equivalent pair.  Records are re-read by all 8 warps of a tile (L1 hits).  Whether the
+// L2 atomic units keep up (~1.8e8 RED per c2 backward) is what the device run has to tell.
+GS_D void half_reduce9(float v[9], int l16) {
+    {
+        const bool h = l16 & 8;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float send = h ? v[i] : v[i + 4], keep = h ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool h = l16 & 4;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float send = h ? v[i] : v[i + 2], keep = h ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool h = l16 & 2;
+        const float send = h ? v[0] : v[1], keep = h ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);  // lanes 2q, 2q+1 of the half: total of value q
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v[8] += __shfl_xor_sync(0xffffffffu, v[8], o);
+}
+
+__global__ void __launch_bounds__(BL_THREADS)
+k_blend_bwd_auto(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
+                 const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
+                 const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
+                 const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
+                 float *__restrict__ d_means2D, float *__restrict__ d_conic_opacity, float *__restrict__ d_rgb) {
+    __shared__ SRec s_stage[BL_WARPS][32];
+    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
+    if (!compute_locally[blockIdx.x]) return;
+    const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Where me = where_am_i(tile, gx);
+    const int px = me.px, py = me.py, l16 = me.l16;
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)py * W + px;
+    final_T += (size_t)view * HW;
+    n_contrib += (size_t)view * HW;
+    dL_dimage += (size_t)view * 3 * HW;
+    const uint2 range = ranges[blockIdx.x];
+    const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
+    const float pxf = (float)px, pyf = (float)py;
+    const float T_final = inside ? final_T[pix] : 0.f;
+    const int last = inside ? (int)n_contrib[pix] : 0;
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+    if (inside) { dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix]; }
+    const float bgdot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
+    const float ddx = 0.5f * (float)W, ddy = 0.5f * (float)H;  // dL/dmeans2D is per NDC unit
+    // What this lane adds after the reduction (it holds the sum with index (l16 >> 1) & 7; odd lanes take the second
+    // output of that sum): target array, element, and the coefficient  kA a' + kB b' + kC c' + kK + kO / opacity.
+    float kA = 0.f, kB = 0.f, kC = 0.f, kK = 0.f, kO = 0.f;
+    float *out = nullptr;
+    int stride = 0;
+    switch (l16) {
+        case 0: out = d_means2D; stride = 2; kA = 2.f * ddx; break;            // sum m dx   -> mean_x
+        case 1: out = d_means2D + 1; stride = 2; kB = ddy; break;              // sum m dx   -> mean_y
+        case 2: out = d_means2D; stride = 2; kB = ddx; break;                  // sum m dy   -> mean_x
+        case 3: out = d_means2D + 1; stride = 2; kC = 2.f * ddy; break;        // sum m dy   -> mean_y
+        case 4: out = d_conic_opacity; stride = 4; kK = -0.5f; break;          // sum m dx^2
+        case 5: out = d_rgb + 2; stride = 3; kK = 1.f; break;                  // blue (value 8, held by every lane)
+        case 6: out = d_conic_opacity + 1; stride = 4; kK = -1.f; break;       // sum m dx dy
+        case 8: out = d_conic_opacity + 2; stride = 4; kK = -0.5f; break;      // sum m dy^2
+        case 10: out = d_conic_opacity + 3; stride = 4; kO = 1.f; break;       // sum m      -> opacity
+        case 12: out = d_rgb; stride = 3; kK = 1.f; break;                     // red
+        case 14: out = d_rgb + 1; stride = 3; kK = 1.f; break;                 // green
+        default: break;
+    }
+    const bool takes_v8 = l16 == 5;
+    const uint32_t stride4 = 4u * (uint32_t)stride;  // bytes between the target elements of consecutive splats
+    uint32_t m = (uint32_t)last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const int wlast = (int)m;  // deepest entry any pixel of this warp reaches
+    const int blkA = me.blk - me.half;
+    const uint32_t half_lanes = me.half ? 0xffff0000u : 0x0000ffffu;
+    SRec *stage = s_stage[warp];
+    float T = T_final, B0 = 0.f, B1 = 0.f, B2 = 0.f;
+    for (int g0 = (wlast - 1) & ~31; g0 >= 0 && wlast > 0; g0 -= 32) {
+        // stage entries g0 .. g0+31 (lane l <- entry g0 + l)
+        const int e = g0 + lane;
+        uint32_t gid = 0u, m16 = 0u;
+        __syncwarp();  // the previous batch's reads of the staging row are done
+        if (e < wlast) {
+            gid = ids[range.x + e];
+            const float4 *r = rec + (size_t)3 * gid;
+            const float4 a = __ldg(r), b = __ldg(r + 1), cc = __ldg(r + 2);
+            stage[lane].a = a; stage[lane].b = b; stage[lane].c = cc;
+            m16 = block_mask16(a.x, a.y, cc.z, cc.w, X0, Y0);
+        }
+        __syncwarp();
+        const uint32_t cA = __ballot_sync(0xffffffffu, (m16 >> blkA) & 1u),
+                       cB = __ballot_sync(0xffffffffu, (m16 >> (blkA + 1)) & 1u);
+        uint32_t mine = me.half ? cB : cA;  // this half-warp's candidates; bit l <-> entry g0 + l
+        const int last_rel = last - g0;     // entry g0 + j is live for this pixel iff j < last_rel
+        while (__any_sync(0xffffffffu, mine != 0u)) {
+            const bool has = mine != 0u;
+            const int j = has ? 31 - __clz(mine) : 0;  // deepest remaining candidate of this half
+            mine &= ~(1u << j);                         // (no-op when !has: mine == 0)
+            const SRec *sr = &stage[j];
+            const float4 a = sr->a, b = sr->b;
+            const float dx = a.x - pxf, dy = a.y - pyf;
+            const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
+            bool ok = (has & (j < last_rel)) & (power >= b.z);   // '&': evaluate everything once, no short circuit
+            if (!__any_sync(0xffffffffu, ok)) continue;
+            const float G = gs_exp_neg(power);
+            const float alpha = fminf(ALPHA_MAX, b.y * G);
+            ok = ok & (power <= 0.f) & (alpha >= ALPHA_MIN);
+            const uint32_t okb = __ballot_sync(0xffffffffu, ok);
+            if (okb == 0u) continue;
+            float v[9];
+            {
+                const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
+                const float ae = ok ? alpha : 0.f;
+                float inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - ae));
+                T = T * inv;
+                const float d0 = b.w - B0, d1 = gb.x - B1, d2 = gb.y - B2;
+                const float dL_dalpha = (d0 * dp0 + d1 * dp1 + d2 * dp2) * T - (T_final * inv) * bgdot;
+                const float mw = ok ? b.y * dL_dalpha * G : 0.f;
+                const float dch = ae * T;
+                B0 += ae * d0; B1 += ae * d1; B2 += ae * d2;
+                const float mx_ = mw * dx, my_ = mw * dy;
+                v[0] = mx_; v[1] = my_; v[2] = mx_ * dx; v[3] = mx_ * dy; v[4] = my_ * dy; v[5] = mw;
+                v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
+            }
+            half_reduce9(v, l16);
+            const uint32_t g = __shfl_sync(0xffffffffu, gid, j);  // splat id of this half's entry
+            if (out != nullptr && (okb & half_lanes) != 0u) {
+                float inv_o;  // opacity >= 1/255 here (alpha >= 1/255 was reached): no denormal handling needed
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_o) : "f"(b.y));
+                const float coef = kA * a.z + kB * a.w + kC * b.x + kK + kO * inv_o;
+                float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + (size_t)g * stride4);
+                atomicAdd(dst, coef * (takes_v8 ? v[8] : v[0]));
+            }
+        }
+    }
+}
+
 int gs_launch_blend_forward(int num_views, int64_t R, int H, int W, const float *rec, const float *bg,
                             const uint8_t *compute_locally, const uint32_t *ranges, const uint32_t *ids_sorted,
                             float *image, float *final_T, uint32_t *n_contrib, int64_t *stats, cudaStream_t stream) {
@@ -641,9 +798,16 @@ extern "C" int gs_render_backward_batched(int num_views, int P, int64_t R, int i
     GS_REQUIRE(rec && bg && compute_locally && ranges && ids_sorted && final_T && n_contrib && dL_dimage, "null input");
     const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     GsStageTimer timer(GS_STAGE_BLEND_BWD, stream);
-    if (g_gs_debug_flags & (GS_DEBUG_BWD_WHT_64 | GS_DEBUG_BWD_WHT_128)) {  // experimental reduction, see above
+    if (g_gs_debug_flags & (GS_DEBUG_BWD_WHT_64 | GS_DEBUG_BWD_WHT_128 | GS_DEBUG_BWD_AUTO)) {  // experimental, see above
         const float4 *r4 = reinterpret_cast<const float4 *>(rec);
         const uint2 *rg = reinterpret_cast<const uint2 *>(ranges);
+        if (g_gs_debug_flags & GS_DEBUG_BWD_AUTO) {
+            k_blend_bwd_auto<<<gx * gy * num_views, BL_THREADS, 0, stream>>>(
+                image_width, image_height, gx * gy, r4, bg, compute_locally, rg, ids_sorted, final_T, n_contrib, dL_dimage,
+                dL_dmeans2D, dL_dconic_opacity, dL_drgb);
+            GS_LAUNCH_CHECK();
+            return GS_OK;
+        }
         if (g_gs_debug_flags & GS_DEBUG_BWD_WHT_64)
             return launch_bwd_wht<64>(gx * gy * num_views, stream, image_width, image_height, gx * gy, r4, bg,
                                       compute_locally, rg, ids_sorted, final_T, n_contrib, dL_dimage, dL_dmeans2D,

@@ -124,6 +124,7 @@ STAGE_NUM = 14
 DEBUG_NO_BLOCK_CULL = 1
 DEBUG_BWD_WHT_64 = 2     # experimental backward kernels (include/grendel_gs_b200.h), off by default
 DEBUG_BWD_WHT_128 = 4
+DEBUG_BWD_AUTO = 8
 
 
 def debug_set(flags):

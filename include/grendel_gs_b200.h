@@ -247,7 +247,10 @@ enum {
      * spent: to be validated (tests/test_gpu_parity.py, GS_B200_EXPERIMENTAL=1) and timed before it may become the
      * default. */
     GS_DEBUG_BWD_WHT_64 = 2,
-    GS_DEBUG_BWD_WHT_128 = 4
+    GS_DEBUG_BWD_WHT_128 = 4,
+    /* EXPERIMENTAL, same status: warp-autonomous gs_render_backward (k_blend_bwd_auto): no CTA barriers, 4x4 blocks per
+     * half-warp, per-(block, splat) global atomics. */
+    GS_DEBUG_BWD_AUTO = 8
 };
 GS_API int gs_debug_set(int flags);
 

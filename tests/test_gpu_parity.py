@@ -153,7 +153,7 @@ def test_render_backward_parity(o32, n, W, H, rad, bg):
 
 @pytest.mark.skipif(__import__("os").environ.get("GS_B200_EXPERIMENTAL") != "1",
                     reason="experimental kernels (off by default): set GS_B200_EXPERIMENTAL=1 to validate them")
-@pytest.mark.parametrize("flag", ["DEBUG_BWD_WHT_64", "DEBUG_BWD_WHT_128"])
+@pytest.mark.parametrize("flag", ["DEBUG_BWD_WHT_64", "DEBUG_BWD_WHT_128", "DEBUG_BWD_AUTO"])
 @pytest.mark.parametrize("n,W,H,rad,bg", [(20000, 320, 200, 7.0, (0.0, 0.0, 0.0)), (3000, 96, 64, 16.0, (0.3, 0.1, 0.7)),
                                           (30000, 200, 120, 9.0, (0.2, 0.5, 0.9))])
 def test_experimental_backward_wht_parity(o32, flag, n, W, H, rad, bg):

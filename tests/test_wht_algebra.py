@@ -73,6 +73,61 @@ def case(rng, far):
     return m, c, ax - px, ay - py, ux, uy
 
 
+def half_reduce9(v):
+    """k_blend_bwd_auto's reduction over the 16 lanes of each half-warp: v is (9, 32); returns (v0, v8) per lane."""
+    v = [x.astype(np.float64).copy() for x in v]
+    l16 = LANE & 15
+    h = (l16 & 8) != 0
+    for i in range(4):
+        send, keep = np.where(h, v[i], v[i + 4]), np.where(h, v[i + 4], v[i])
+        v[i] = keep + shfl_xor(send, 8)
+    h = (l16 & 4) != 0
+    for i in range(2):
+        send, keep = np.where(h, v[i], v[i + 2]), np.where(h, v[i + 2], v[i])
+        v[i] = keep + shfl_xor(send, 4)
+    h = (l16 & 2) != 0
+    send, keep = np.where(h, v[0], v[1]), np.where(h, v[1], v[0])
+    v[0] = keep + shfl_xor(send, 2)
+    v[0] = v[0] + shfl_xor(v[0], 1)
+    for o in (8, 4, 2, 1):
+        v[8] = v[8] + shfl_xor(v[8], o)
+    return v[0], v[8]
+
+
+def test_half_warp_reduction_and_lane_roles_of_the_autonomous_kernel():
+    """Each half-warp reduces its own nine sums; the lane roles (target element + coefficient) of k_blend_bwd_auto turn
+    them into exactly the gradient terms the default kernel's flush writes."""
+    rng = np.random.default_rng(3)
+    ddx, ddy = 960.0, 540.0
+    # l16 -> (target, kA, kB, kC, kK, kO, takes_v8): the switch in the kernel
+    roles = {0: ("mean_x", 2 * ddx, 0, 0, 0, 0, False), 1: ("mean_y", 0, ddy, 0, 0, 0, False),
+             2: ("mean_x", 0, ddx, 0, 0, 0, False), 3: ("mean_y", 0, 0, 2 * ddy, 0, 0, False),
+             4: ("conic_x", 0, 0, 0, -0.5, 0, False), 5: ("blue", 0, 0, 0, 1.0, 0, True),
+             6: ("conic_y", 0, 0, 0, -1.0, 0, False), 8: ("conic_z", 0, 0, 0, -0.5, 0, False),
+             10: ("opacity", 0, 0, 0, 0, 1.0, False), 12: ("red", 0, 0, 0, 1.0, 0, False),
+             14: ("green", 0, 0, 0, 1.0, 0, False)}
+    for _ in range(100):
+        v = rng.normal(size=(9, 32))
+        # every half-warp works on its own splat: a', b', c', opacity
+        rec = rng.normal(size=(2, 4))
+        rec[:, 3] = rng.uniform(0.05, 0.9, 2)
+        v0, v8 = half_reduce9(v)
+        for half in range(2):
+            lanes = slice(16 * half, 16 * half + 16)
+            s = v[:, lanes].sum(axis=1)
+            ap, bp, cp, o = rec[half]
+            want = {"mean_x": (2 * ap * s[0] + bp * s[1]) * ddx, "mean_y": (2 * cp * s[1] + bp * s[0]) * ddy,
+                    "conic_x": -0.5 * s[2], "conic_y": -s[3], "conic_z": -0.5 * s[4], "opacity": s[5] / o,
+                    "red": s[6], "green": s[7], "blue": s[8]}
+            got = {k: 0.0 for k in want}
+            for l16, (tgt, kA, kB, kC, kK, kO, use8) in roles.items():
+                lane = 16 * half + l16
+                coef = kA * ap + kB * bp + kC * cp + kK + kO / o
+                got[tgt] += coef * (v8[lane] if use8 else v0[lane])
+            for k in want:
+                assert abs(got[k] - want[k]) <= 1e-9 * (1 + abs(want[k])), (k, got[k], want[k])
+
+
 def test_slots_are_a_bijection_onto_16():
     slots = [slot_of(int(L)) for L in LANE]
     assert sorted(s for s in slots if s >= 0) == list(range(16))
