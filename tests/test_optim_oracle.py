@@ -46,8 +46,9 @@ def check(got, ref, lr, what):
     # exp_avg is a signed running mean: entries that nearly cancel carry the absolute rounding of their larger terms
     np.testing.assert_allclose(m, rm, rtol=2e-6, atol=2e-7 * float(np.abs(rm).max()), err_msg=what + " exp_avg")
     np.testing.assert_allclose(v, rv, rtol=2e-6, atol=1e-20, err_msg=what + " exp_avg_sq")
+    # p: the update itself is ~lr and agrees to ~1e-5 of that; the final rounding of p can flip by an ulp per step
     err = np.abs(p - rp)
-    assert (err <= 4e-6 * lr * 10 + 2.4e-7 * np.abs(rp)).all(), (what, float(err.max()))
+    assert (err <= 4e-5 * lr + 6e-7 * np.abs(rp)).all(), (what, float(err.max()))
 
 
 def test_adam_oracle_matches_torch_adam_on_cpu():
