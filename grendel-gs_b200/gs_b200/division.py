@@ -89,6 +89,39 @@ class StrategyHistory:
         self.history.append([[s.camera_uid, s.gpu_ids, s.division_pos] for s in strategies])
 
 
+def running_time_of(stats_collector):
+    """The cost the reference charges a (rank, camera) pair: forward + backward render time + 2 x loss time
+    (workload_division.py:953-957); milliseconds."""
+    return (float(stats_collector["forward_render_time"]) + float(stats_collector["backward_render_time"]) +
+            2.0 * float(stats_collector.get("forward_loss_time", 0.0)))
+
+
+def heuristics_update_enabled(iteration, world_size, bsz, image_height, image_width, adjust_strategy_warmup_iterations=-1,
+                              no_heuristics_update=False):
+    """finish_strategy_final's gate (workload_division.py:967-978): the row costs are only re-estimated after the warm-up,
+    on more than one rank, and NOT when every rank can be handed whole images of at most 1080p (bsz >= world size) or the
+    images are small (<= 600 x 1000) -- there the uniform split stays."""
+    if iteration <= adjust_strategy_warmup_iterations or world_size == 1 or no_heuristics_update:
+        return False
+    if bsz >= world_size and (image_height <= 1080 or image_width <= 1920):
+        return False
+    if image_height <= 600 or image_width <= 1000:
+        return False
+    return True
+
+
+def finish_strategy(history, strategies, gpu_camera_running_time, iteration, world_size, image_height, image_width,
+                    heuristic_decay=0.0, adjust_strategy_warmup_iterations=-1, no_heuristics_update=False):
+    """finish_strategy_final (workload_division.py:944-998) after the times have been all-gathered:
+    gpu_camera_running_time[gpu][camera] in ms (-1 where the rank did not render the camera).  Returns True if the
+    heuristic was updated (the next start_strategy then moves the strip boundaries)."""
+    if not heuristics_update_enabled(iteration, world_size, len(strategies), image_height, image_width,
+                                     adjust_strategy_warmup_iterations, no_heuristics_update):
+        return False
+    history.update(strategies, gpu_camera_running_time, heuristic_decay)
+    return True
+
+
 def start_strategy(camera_uids, history, world_size, global_rank, border_divpos_coeff=1.0, local_sampling=False):
     """-> (strategies per camera, gpuid2tasks[gpu] = [(camera index, row_l, row_r), ...])."""
     tile_y = history.tile_y

@@ -76,6 +76,27 @@ def test_history_update_rebalances():
     assert s2[0].division_pos[1] < 32
 
 
+def test_finish_strategy_gate_follows_the_reference():
+    """workload_division.py:967-978: no re-estimation during warm-up, on one rank, when every rank can take whole images
+    of at most 1080p, or for small images; otherwise the measured times move the boundaries."""
+    en = division.heuristics_update_enabled
+    assert not en(iteration=5, world_size=4, bsz=1, image_height=2160, image_width=3840, adjust_strategy_warmup_iterations=10)
+    assert not en(iteration=50, world_size=1, bsz=1, image_height=2160, image_width=3840)
+    assert not en(iteration=50, world_size=4, bsz=1, image_height=2160, image_width=3840, no_heuristics_update=True)
+    assert not en(iteration=50, world_size=4, bsz=4, image_height=1080, image_width=1920)      # the bench configuration
+    assert not en(iteration=50, world_size=4, bsz=1, image_height=600, image_width=800)
+    assert en(iteration=50, world_size=4, bsz=1, image_height=1080, image_width=1920)          # one image over 4 ranks
+    assert en(iteration=50, world_size=8, bsz=8, image_height=2160, image_width=3840)          # config c4
+    assert division.running_time_of({"forward_render_time": 1.0, "backward_render_time": 2.0, "forward_loss_time": 0.5}) == 4.0
+    hist = division.StrategyHistory([3], 135, 2)
+    st, _ = division.start_strategy([3], hist, 2, 0)
+    assert not division.finish_strategy(hist, st, [[9.0], [3.0]], iteration=1, world_size=2, image_height=1080,
+                                        image_width=1920, adjust_strategy_warmup_iterations=5)
+    assert division.start_strategy([3], hist, 2, 0)[0][0].division_pos == st[0].division_pos
+    assert division.finish_strategy(hist, st, [[9.0], [3.0]], iteration=9, world_size=2, image_height=2160, image_width=3840)
+    assert division.start_strategy([3], hist, 2, 0)[0][0].division_pos[1] < st[0].division_pos[1]
+
+
 def test_local_sampling_gives_whole_images():
     hist = division.StrategyHistory([0, 1, 2, 3], 30, 2)
     strategies, tasks = division.start_strategy([0, 1, 2, 3], hist, 2, 1, local_sampling=True)
