@@ -21,7 +21,10 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
         if lr < 0.0 or eps < 0.0 or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
             raise ValueError("invalid Adam hyper-parameters")
-        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps))
+        # the option keys torch.optim.Adam keeps in its groups, at the values this kernel implements: a state_dict
+        # written here loads into torch.optim.Adam (load_state_dict REPLACES the groups by the saved ones) and back
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=0.0, amsgrad=False, maximize=False,
+                                      foreach=None, capturable=False, differentiable=False, fused=None))
         self.grad_scale = float(grad_scale)
 
     @torch.no_grad()
@@ -36,6 +39,9 @@ class FusedAdam(torch.optim.Optimizer):
         todo = []
         for group in self.param_groups:
             b1, b2 = group["betas"]
+            if group.get("weight_decay", 0.0) != 0.0 or group.get("amsgrad", False) or group.get("maximize", False):
+                raise NotImplementedError("FusedAdam implements plain Adam only (weight_decay=0, amsgrad=False, maximize=False)"
+                                          " -- what the reference configures, scene/gaussian_model.py:292")
             for p in group["params"]:
                 if p.grad is None:
                     continue

@@ -83,9 +83,25 @@ def test_fused_adam_has_no_cpu_path_and_torch_state_layout():
     params[0].grad = torch.ones_like(params[0])
     with pytest.raises(TypeError):               # CPU tensors are rejected, never updated on the host
         opt.step()
-    ref = torch.optim.Adam(make(8, 1)[1], lr=0.0, eps=1e-15)
+    ref_params, ref_groups = make(8, 1)
+    ref = torch.optim.Adam(ref_groups, lr=0.0, eps=1e-15)
     assert opt.state_dict()["param_groups"][0].keys() >= {"lr", "betas", "eps", "params", "name"}
-    opt.load_state_dict(ref.state_dict())        # a checkpoint written by the reference's optimizer loads
+    # a checkpoint written by the reference's optimizer (with state) loads into FusedAdam ...
+    for p in ref_params:
+        p.grad = torch.ones_like(p)
+    ref.step()
+    opt.load_state_dict(ref.state_dict())
+    st = opt.state[opt.param_groups[2]["params"][0]]
+    assert int(st["step"]) == 1 and st["exp_avg"].shape == ref_params[2].shape
+    # ... and one written by FusedAdam loads into torch.optim.Adam, which can then step (load_state_dict replaces the
+    # groups by the saved ones, so they must carry every key torch's step reads)
+    back = torch.optim.Adam(make(8, 1)[1], lr=0.0, eps=1e-15)
+    back.load_state_dict(opt.state_dict())
+    for g in back.param_groups:
+        for p in g["params"]:
+            p.grad = torch.ones_like(p)
+    back.step()
+    assert int(back.state[back.param_groups[0]["params"][0]]["step"]) == 2
 
 
 def test_adam_oracle_sqrt_lr_scaling_betas():
