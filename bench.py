@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--n", type=int, default=0, help="override Gaussian count")
     ap.add_argument("--cpu-sample", type=int, default=250_000, help="Gaussians in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--time-optimizer", action="store_true",
+                    help="also time the fused Adam step (gs_adam_step) on the rank's parameters, reported separately under "
+                         "'optimizer' (the headline metric excludes the optimizer, SURVEY.md 8d)")
     return ap.parse_args()
 
 
@@ -262,6 +265,31 @@ def run_ours(args):
     ms_e2e = float(t.item()) / steps
     h2d, d2h = trainer.io_bytes_per_step()
 
+    # ---- optional: the fused Adam step on this rank's six parameter tensors, after both timed regions ------------
+    optimizer = None
+    if args.time_optimizer:
+        from gs_b200.optim import FusedAdam
+        p = trainer.params
+        lrs = {"_xyz": 0.00016, "_features_dc": 0.0025, "_features_rest": 0.0025 / 20, "_opacity": 0.05, "_scaling": 0.005,
+               "_rotation": 0.001}            # arguments/__init__.py:110-119
+        opt = FusedAdam([{"params": [getattr(p, k)], "lr": v, "name": k} for k, v in lrs.items()], lr=0.0, eps=1e-15)
+        trainer.step(resident=True)           # leaves gradients in place
+        for _ in range(3):
+            opt.step(grad_scale=1.0 / B)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a0.record()
+        n_opt = 20
+        for _ in range(n_opt):
+            opt.step(grad_scale=1.0 / B)
+        a1.record()
+        torch.cuda.synchronize()
+        adam_ms = a0.elapsed_time(a1) / n_opt
+        elems = sum(t.numel() for t in p.raw_parameters())
+        optimizer = {"kernel": "k_adam (gs_adam_step)", "ms_per_step": adam_ms, "elements": elems,
+                     "alg_bytes": 28 * elems, "achieved_gbs": 28 * elems / (adam_ms * 1e-3) / 1e9,
+                     "note": "one launch for the six parameter tensors incl. the 1/bsz gradient scaling; not part of value/e2e"}
+
     # ---- diagnostics, OUTSIDE both timed regions: wall clock per phase with a device synchronise after each phase
     # (serialises host and device, so the phases add up to more than ms_per_step; max over ranks) ----------------
     phase_ms = None
@@ -340,6 +368,9 @@ def run_ours(args):
             "roofline": roofline, "clocks": clocks}
     if debug_flags:
         line["config"]["debug_flags"] = debug_flags
+    if optimizer is not None:
+        optimizer["frac_of_hbm_peak"] = optimizer["achieved_gbs"] / peak
+        line["optimizer"] = optimizer
     if phase_ms is not None:  # multi-GPU only; measured outside the timed regions (see above)
         line["phase_ms_serialised"] = phase_ms
         line["config"]["exchange"] = ("NVLink peer-memory stores fused into the pack kernels (gs_xchg_pack_p2p)"
