@@ -62,6 +62,9 @@ SIGNATURES = {
     "gs_xchg_pack_grad": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "gs_xchg_scatter_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_adam_step": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp]),
+    "gs_densify_temp_bytes": (_sz, [_i]),
+    "gs_densify_select": (_i, [_i, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp, _sz, _vp, _vp]),
+    "gs_densify_gather": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p), _vp]),
     "gs_peer_open": (_i, [_vp, C.POINTER(C.c_void_p)]),
     "gs_peer_close": (_i, [_vp]),

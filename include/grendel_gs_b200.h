@@ -373,6 +373,28 @@ GS_API int gs_adam_step(int num_tensors, const int64_t *numel_host, void *const 
                         const double *lr_host, const double *beta1_host, const double *beta2_host,
                         const double *eps_host, const int64_t *step_host, float grad_scale, void *stream);
 
+/* ---- densification step -- /root/reference/scene/gaussian_model.py:1005-1044 ------------------
+ * densify_and_prune = densify_and_clone (:973-1003) + densify_and_split (:922-971) + prune_points (:816-835) over the
+ * six parameters and both Adam moments (cat_tensors_to_optimizer :837-881, _prune_optimizer :789-814), ~150 torch
+ * kernels and a dozen host read-backs in the reference.  Here: gs_densify_select computes every Gaussian's decisions
+ * and ONE scan that yields the output row of every survivor / clone / split child (order of the reference's end state:
+ * survivors, clones, children copy 1, children copy 2; each in index order) and reads six counts back;
+ * gs_densify_gather then writes every tensor once (moments of new Gaussians zero, children: position
+ * R(q)(s * z) + x from caller-provided standard-normal draws z, log-scale log(s / 1.6)).
+ * counts_host: HOST int32[6] = kept, clones, children copy 1, children copy 2, S (split-selected; the split reads
+ * 2 S rows of noise), new number of Gaussians.  scaling_raw / opacity_raw / rotation_raw are the raw parameters
+ * (log-scale, logit, unnormalised quaternion).  Written after round 1's device budget was spent: NOT yet run on a GPU. */
+GS_API size_t gs_densify_temp_bytes(int P);
+GS_API int gs_densify_select(int P, const float *xyz_gradient_accum, const float *denom, const float *scaling_raw,
+                             const float *opacity_raw, float max_grad, float min_opacity, float extent,
+                             float percent_dense, int use_screen_size, void *temp, size_t temp_bytes,
+                             int32_t *counts_host, void *stream);
+/* src_host / dst_host: HOST arrays of num_tensors (<= 24) device pointers to (P, width) inputs / (new_P, width) outputs of
+ * 4-byte elements; kind_host: 0 copy, 1 position (width 3), 2 log-scale (width 3), 3 Adam moment. */
+GS_API int gs_densify_gather(int P, int S, int new_P, int num_tensors, const void *const *src_host, void *const *dst_host,
+                             const int32_t *width_host, const int32_t *kind_host, const float *scaling_raw,
+                             const float *rotation_raw, const float *noise, const void *temp, void *stream);
+
 /* ---- legacy tile-mask / tile-exchange helpers (dead code in the shipped trainer) ------
  * _C.get_touched_locally                     -- gaussian_renderer/loss_distribution.py:136-141
  * _C.get_pixels_compute_locally_and_in_rect  -- loss_distribution.py:205-213
