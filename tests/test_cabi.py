@@ -58,6 +58,39 @@ def test_constants_and_version(lib):
     assert b"null" in lib.gs_last_error().lower()
 
 
+def test_argument_errors_are_reported_not_crashed(lib):
+    """Every entry point validates its arguments before the first CUDA call and reports through the return code +
+    gs_last_error() (the reference side sees a Python exception, never a crash or an exit): exercised here, without a GPU,
+    on the entry points added for batches, the peer exchange, Adam and densification."""
+    from gs_b200 import _lib
+    i32, vp = ctypes.c_int32, ctypes.c_void_p
+    R = ctypes.c_int64(0)
+    one = (i32 * 2)(0, 0)
+    bad = [
+        ("gs_render_count_batched", (0, one, 16, 16, None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(R), None)),
+        ("gs_render_count_batched", (65, one, 16, 16, None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(R), None)),
+        ("gs_render_count_batched", (1, (i32 * 2)(3, 5), 16, 16, None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(R), None)),
+        ("gs_render_backward_batched", (0, 0, 0, 16, 16, None, None, None, None, None, None, None, None, None, None, None, None)),
+        ("gs_loss_forward_batched", (1, 16, 16, None, None, None, None, None, 0, None)),
+        ("gs_xchg_pack_p2p", (0, 4, 2, None, None, None, None, None, None, None, None, None, None)),
+        ("gs_xchg_pack_grad_p2p", (1, None, None, None, None, 8, 1, None, None, None, None, None)),
+        ("gs_peer_alloc", (0, None, None)),
+        ("gs_peer_open", (None, None)),
+        ("gs_adam_step", (9, None, None, None, None, None, None, None, None, None, None, ctypes.c_float(1.0), None)),
+        ("gs_adam_step", (1, None, None, None, None, None, None, None, None, None, None, ctypes.c_float(1.0), None)),
+        ("gs_densify_select", (0, None, None, None, None, ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(1), ctypes.c_float(0.01), 0, None, 0, None, None)),
+        ("gs_densify_gather", (4, 0, 4, 25, None, None, None, None, None, None, None, None, None)),
+    ]
+    for name, args in bad:
+        rc = getattr(lib, name)(*args)
+        assert rc == -1, (name, rc)                       # GS_EINVAL
+        assert len(lib.gs_last_error()) > 10, name
+        with pytest.raises(_lib.GsError):
+            _lib.call(name, *args)
+    assert lib.gs_debug_set(0) == 0 and lib.gs_debug_set(0) == 0
+    assert lib.gs_adam_step(0, None, None, None, None, None, None, None, None, None, None, ctypes.c_float(1.0), None) == 0
+
+
 def test_dropin_package_exports_reference_names():
     import diff_gaussian_rasterization as d
     import gsplat
