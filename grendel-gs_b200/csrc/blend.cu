@@ -393,13 +393,16 @@ k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
 // moments about the block origin are linear combinations of the 16 coefficients with popc(L) <= 2:
 //     sum m b_i     = (W_0 - W_{e_i}) / 2          sum m b_i b_j = (W_0 - W_{e_i} - W_{e_j} + W_{e_i + e_j}) / 4
 // The 16 lanes that hold them store them (one STS), the flush thread of the splat forms the moments and shifts them to
-// the splat centre.  The three colour sums take a 4-value transposing butterfly (6 SHFL).  30 instructions instead of
-// 51, at the price of 19 instead of 9 floats of shared memory per (warp, entry) -- hence the CHUNK parameter: 64
-// entries keep 5 CTAs per SM, 128 entries halve the barriers but leave 2 CTAs per SM.  To be timed on the device.
+// the splat centre.  The three colour sums take a 4-value transposing butterfly (6 SHFL).  92-98 instead of 111
+// instructions per pair (profiles/r1_sass_blend_bwd.md), at the price of 19 instead of 9 floats of shared memory per
+// (warp, entry) -- hence the CHUNK parameter: 64 entries fit 4 CTAs per SM, 128 entries halve the barriers but leave 2
+// CTAs per SM.  To be timed on the device.
 #define BWH_NVAL 19
 
 template <int CHUNK>
-__global__ void __launch_bounds__(BL_THREADS, CHUNK == 64 ? 5 : 2)   // 44 KB / 83 KB of shared memory per CTA
+// 44 KB / 83 KB of shared memory per CTA allow 5 / 2 CTAs per SM; the 64-entry variant is built for 4: squeezing it into
+// 48 registers for 5 costs 23 more instructions per pair (114 vs 91) in rematerialised addresses
+__global__ void __launch_bounds__(BL_THREADS, CHUNK == 64 ? 4 : 2)
 k_blend_bwd_wht(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
                 const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
                 const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
