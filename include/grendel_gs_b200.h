@@ -395,6 +395,12 @@ GS_API int gs_densify_gather(int P, int S, int new_P, int num_tensors, const voi
                              const int32_t *width_host, const int32_t *kind_host, const float *scaling_raw,
                              const float *rotation_raw, const float *noise, const void *temp, void *stream);
 
+/* ---- simple_knn._C.distCUDA2 -- /root/reference/scene/gaussian_model.py:20,163-166 ------------------------------------
+ * Mean squared distance of every point to its 3 nearest OTHER points (self excluded by index, duplicates count at
+ * distance 0; fewer than 3 other points: the mean of those that exist), the start-up scale initialisation.  Exact, by
+ * tiled brute force (init-time only).  points (N,3) fp32 -> mean_dist2 (N) fp32.  NOT yet run on a device. */
+GS_API int gs_knn3_mean_dist2(int N, const float *points, float *mean_dist2, void *stream);
+
 /* ---- legacy tile-mask / tile-exchange helpers (dead code in the shipped trainer) ------
  * _C.get_touched_locally                     -- gaussian_renderer/loss_distribution.py:136-141
  * _C.get_pixels_compute_locally_and_in_rect  -- loss_distribution.py:205-213

@@ -20,7 +20,7 @@ def main():
     env = dict(os.environ, GS_B200_EXPERIMENTAL="1")
     ok = {}
     # 0. everything else that was written without device access: fused Adam, fused densification step
-    for f in ("test_zz_fused_adam_gpu.py", "test_zz_densify_gpu.py"):
+    for f in ("test_zz_fused_adam_gpu.py", "test_zz_densify_gpu.py", "test_zz_knn_gpu.py"):
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", f), "-q", "-m", "gpu"], env=env,
                            capture_output=True, text=True, cwd=ROOT)
         print(f"[ab] {f}: {'PASS' if r.returncode == 0 else 'FAIL'}  {r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''}",
