@@ -1,4 +1,4 @@
-"""-m gpu (gated: GS_B200_EXPERIMENTAL=1 -- written without device access, first validated in round 2):
+"""-m gpu:
 gs_densify_select / gs_densify_gather through gs_b200.densify.densify_and_prune against tests/golden/densify.npz, i.e.
 against the REFERENCE's own densify_and_prune run (tests/golden/make_densify_golden.py), with the same normal draws."""
 import os
@@ -9,9 +9,7 @@ import torch
 
 from test_densify_oracle import load
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("GS_B200_EXPERIMENTAL") != "1",
-                                 reason="not yet validated on a device: set GS_B200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 NAMES = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
 
 

@@ -1,5 +1,7 @@
 """-m gpu: gs_adam_step (through gs_b200.optim.FusedAdam) against the CPU restatement (oracle/adam_oracle.py, itself
 pinned to torch.optim.Adam on CPU) and against torch.optim.Adam running on the same device."""
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -55,9 +57,11 @@ def test_fused_adam_state_is_interchangeable_with_torch_adam():
         for a, b in zip(params_t, params_f):
             a.copy_(b)
     ref = torch.optim.Adam(groups_t, lr=0.0, eps=1e-15)
-    ref.load_state_dict(fused.state_dict())
+    # load_state_dict keeps tensors whose dtype/device already match (no copy): deepcopy, or the optimizers would
+    # share exp_avg / exp_avg_sq / step and both step() calls would advance the same moments
+    ref.load_state_dict(copy.deepcopy(fused.state_dict()))
     back = FusedAdam(groups_f, lr=0.0, eps=1e-15)
-    back.load_state_dict(ref.state_dict())
+    back.load_state_dict(copy.deepcopy(ref.state_dict()))
     for p, q, g in zip(params_f, params_t, grads_for(params_f, 3, 0.1)):
         p.grad, q.grad = g.clone(), g.clone()
     back.step()

@@ -1,4 +1,4 @@
-"""-m gpu (gated: GS_B200_EXPERIMENTAL=1 -- written without device access): gs_knn3_mean_dist2 against a numpy brute
+"""-m gpu: gs_knn3_mean_dist2 against a numpy brute
 force (the definition: exact 3 nearest OTHER points, duplicates count at distance 0) and against the torch shim."""
 import os
 
@@ -6,9 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("GS_B200_EXPERIMENTAL") != "1",
-                                 reason="not yet validated on a device: set GS_B200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 def brute(p):
