@@ -26,6 +26,14 @@
 //     (splat, tile) -- instead of 9 atomics per (splat, pixel) in the classical design.  The per-pixel state is
 //     just (T, behind-colour B): lanes that skip a splat run the same instructions with alpha = 0, which makes
 //     every update a no-op, so the blend path has no per-lane branches or conditional moves.
+//
+// Round 2: SEGMENT-PARALLEL backward (k_blend_bwd_seg, the default).  The forward stores, for every pixel of a tile, a
+// checkpoint (T, colour summed over the LATER segments) every SEG_K entries of the tile list, so every (tile, SEG_K-entry
+// segment) can be walked back to front on its own.  One WARP owns one such unit and ALL 256 pixels of the tile: lane l
+// holds pixel l of each of the eight 8x4 blocks (state T and S = sum of the colour behind, weighted with dL/dpixel, in
+// registers), loops over the blocks the splat can reach, accumulates the nine gradient sums in registers ACROSS the
+// blocks, reduces them ONCE per (splat, tile) with the 9-value butterfly and issues one RED set straight away: no CTA
+// barrier, no shared partial sums, no flush pass, 1 instead of ~1.9 reductions per (splat, tile).
 #include "common.cuh"
 
 #define BL_THREADS 256
@@ -76,15 +84,45 @@ GS_D uint32_t block_mask16(float mx, float my, float ex, float ey, float X0, flo
 // staged splat: one 48-byte slot so a single address feeds all three shared-memory loads
 struct __align__(16) SRec { float4 a; float4 b; float4 c; };
 
-template <bool STATS>
+// ---- segment workspace shared by the forward (writer) and the segment-parallel backward (reader) -------------------
+// SEG_K entries per segment.  Checkpoint slot of (tile t, boundary after segment s) = ranges[t].x / SEG_K + t + s:
+// injective over all tiles without a scan (floor((x+l)/K) - floor(x/K) >= ceil(l/K) - 1), < R / SEG_K + T + 1.
+// A slot holds one float4 per pixel, in the BACKWARD's order: index = (8x4 block) * 32 + lane.
+#define SEG_K 64
+#define SEG_SLOT 256
+struct SegWs {
+    uint32_t *n_units;    // [1] number of (tile, segment) units appended by the forward
+    uint32_t *tile_last;  // [T] deepest contributing entry of the tile (max n_contrib over its pixels)
+    uint2 *units;         // [R / SEG_K + T] (tile, segment)
+    float4 *ckpt;         // [(R / SEG_K + T + 1) * SEG_SLOT]
+};
+static size_t seg_align(size_t v) { return (v + 255) / 256 * 256; }
+static size_t seg_bytes(int64_t R, int64_t T) {
+    const size_t slots = (size_t)(R / SEG_K + T + 1);
+    return 256 + seg_align((size_t)T * 4) + seg_align(slots * sizeof(uint2)) + slots * SEG_SLOT * sizeof(float4);
+}
+static SegWs seg_carve(void *ws, int64_t R, int64_t T) {
+    const size_t slots = (size_t)(R / SEG_K + T + 1);
+    char *p = (char *)ws;
+    SegWs w;
+    w.n_units = (uint32_t *)p; p += 256;
+    w.tile_last = (uint32_t *)p; p += seg_align((size_t)T * 4);
+    w.units = (uint2 *)p; p += seg_align(slots * sizeof(uint2));
+    w.ckpt = (float4 *)p;
+    return w;
+}
+extern "C" size_t gs_render_seg_bytes(int64_t R, int num_tiles) { return seg_bytes(R > 0 ? R : 0, num_tiles > 0 ? num_tiles : 0); }
+
+template <bool STATS, bool CKPT>
 __global__ void __launch_bounds__(BL_THREADS)
 k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
             const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
             const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
-            uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats) {
+            uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats, const SegWs seg) {
     __shared__ SRec s_rec[FW_CHUNK];
     __shared__ uint16_t s_cull[FW_CHUNK];
     __shared__ unsigned long long s_stats[3];
+    __shared__ uint32_t s_red[BL_WARPS + 2];
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
     // blockIdx.x = view * tiles_per_view + tile: the views' tile arrays and images are concatenated (GsViews)
     const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
@@ -99,6 +137,7 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
     n_contrib += (size_t)view * HW;
     if (!compute_locally[blockIdx.x]) {  // non-local tiles must read exactly 0 (loss_distribution.py:1875)
         if (inside) { image[pix] = 0.f; image[HW + pix] = 0.f; image[2 * HW + pix] = 0.f; }
+        if (CKPT && threadIdx.x == 0) seg.tile_last[blockIdx.x] = 0u;
         return;
     }
     const uint2 range = ranges[blockIdx.x];
@@ -106,10 +145,18 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
     const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
     const float qnan = __int_as_float(0x7fc00000);
     float pxf = inside ? (float)px : qnan, pyf = (float)py;  // NaN coordinates: the pixel never passes a test
-    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    // colour is accumulated per SEG_K-entry segment (C) and folded front to back into Ctot at every segment boundary --
+    // the same arithmetic with and without checkpoints, so both forward variants produce identical images
+    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Ct0 = 0.f, Ct1 = 0.f, Ct2 = 0.f;
     uint32_t last = 0, blended = 0, considered = 0;
     bool done = !inside;
     const int blkA = me.blk - me.half;  // block of lanes 0-15; lanes 16-31 own blkA + 1
+    // this pixel's entry in a checkpoint slot: (8x4 block = warp) * 32 + (row in block) * 8 + (column in block)
+    float4 *ck = nullptr;
+    int nck = 0;
+    if (CKPT)
+        ck = seg.ckpt + ((size_t)(range.x / SEG_K) + blockIdx.x) * SEG_SLOT + (threadIdx.x >> 5) * 32 + (me.l16 >> 2) * 8 +
+             me.half * 4 + (me.l16 & 3);
     for (int base = 0; base < total; base += FW_CHUNK) {
         if (__syncthreads_count(done) == BL_THREADS) break;
         const int cnt = min(FW_CHUNK, total - base);
@@ -123,6 +170,14 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {
             if (__all_sync(FULL, done)) break;  // checked once per 32 entries; finished pixels are NaN anyway
+            {   // segment boundary: a pixel that is still alive here has its warp here, so its checkpoint gets written
+                const int e0 = base + g0;
+                if (e0 > 0 && (e0 & (SEG_K - 1)) == 0) {
+                    if (CKPT) { ck[(size_t)nck * SEG_SLOT] = make_float4(T, C0, C1, C2); nck++; }
+                    Ct0 += C0; Ct1 += C1; Ct2 += C2;
+                    C0 = C1 = C2 = 0.f;
+                }
+            }
             const int jj = g0 + lane;
             const uint32_t m = jj < cnt ? (uint32_t)s_cull[jj] : 0u;
             const uint32_t cA = __ballot_sync(FULL, (m >> blkA) & 1u), cB = __ballot_sync(FULL, (m >> (blkA + 1)) & 1u);
@@ -159,12 +214,40 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
         }
     }
     if (inside) {
-        image[pix] = C0 + T * bg[0];
-        image[HW + pix] = C1 + T * bg[1];
-        image[2 * HW + pix] = C2 + T * bg[2];
+        image[pix] = (Ct0 + C0) + T * bg[0];
+        image[HW + pix] = (Ct1 + C1) + T * bg[1];
+        image[2 * HW + pix] = (Ct2 + C2) + T * bg[2];
         final_T[pix] = T;
         n_contrib[pix] = last;
         if (considered == 0) considered = (uint32_t)total;
+    }
+    if (CKPT) {
+        // checkpoint s so far = (T, colour of segment s); the backward wants (T, colour of all LATER segments): suffix sums,
+        // added back to front (small terms first, no cancellation)
+        float r0 = C0, r1 = C1, r2 = C2;
+        for (int s = nck - 1; s >= 0; s--) {
+            const float4 c = ck[(size_t)s * SEG_SLOT];
+            ck[(size_t)s * SEG_SLOT] = make_float4(c.x, r0, r1, r2);
+            r0 += c.y; r1 += c.z; r2 += c.w;
+        }
+        // the tile's units for the backward: segments [0, ceil(deepest contributor / SEG_K))
+        uint32_t m = inside ? last : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+        if (lane == 0) s_red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tl = 0;
+#pragma unroll
+            for (int w = 0; w < BL_WARPS; w++) tl = max(tl, s_red[w]);
+            const uint32_t nseg = (tl + SEG_K - 1) / SEG_K;
+            seg.tile_last[blockIdx.x] = tl;
+            s_red[BL_WARPS] = nseg;
+            s_red[BL_WARPS + 1] = nseg ? atomicAdd(seg.n_units, nseg) : 0u;
+        }
+        __syncthreads();
+        const uint32_t nseg = s_red[BL_WARPS], ubase = s_red[BL_WARPS + 1];
+        for (uint32_t i = threadIdx.x; i < nseg; i += BL_THREADS) seg.units[ubase + i] = make_uint2(blockIdx.x, nseg - 1 - i);
     }
     if (STATS) {  // stages 81-83: sums of tile-list length / entries walked / entries blended
         if (threadIdx.x < 3) s_stats[threadIdx.x] = 0ull;
@@ -183,7 +266,8 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
     }
 }
 
-// ---- backward -------------------------------------------------------------------------------------------
+// ---- backward, tile-parallel (round 1; kept behind gs_debug_set(GS_DEBUG_BWD_TILE) and for callers without a segment
+// workspace) ----------------------------------------------------------------------------------------------------------
 // The backward keeps one 8x4 pixel block per FULL warp (8-bit cull mask, 128-entry chunks): the half-warp /
 // 4x4 layout that helps the forward was measured slower here (2.18 vs 1.77 ms on c2) -- sixteen private
 // partial-sum slots force 64-entry chunks, and the extra barriers + 64-thread flush cost more (barrier stalls
@@ -384,393 +468,197 @@ k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
     }
 }
 
-// ---- backward, EXPERIMENTAL variant (off by default; gs_debug_set(GS_DEBUG_BWD_WHT_64 / _128)) ---------------------
-// Same walk, same per-pixel arithmetic; only the lane -> warp reduction of the six moments differs.  SASS of
-// k_blend_bwd: 110 instructions per fully processed (warp, splat) pair, 51 of them forming and reducing the nine sums
-// (14 SHFL + 14 FSEL + 14 FADD + 9 FMUL).  Here the per-pixel weight m alone goes through a 5-stage Walsh-Hadamard
-// butterfly (5 SHFL + 5 FFMA): afterwards lane L holds W_L = sum_l m_l (-1)^popc(L & l).  A pixel's offset inside the
-// warp's 8x4 block is a polynomial of degree <= 2 in the lane bits (lx = b0 + 2 b1 + 4 b2, ly = b3 + 2 b4), so all six
-// moments about the block origin are linear combinations of the 16 coefficients with popc(L) <= 2:
-//     sum m b_i     = (W_0 - W_{e_i}) / 2          sum m b_i b_j = (W_0 - W_{e_i} - W_{e_j} + W_{e_i + e_j}) / 4
-// The 16 lanes that hold them store them (one STS), the flush thread of the splat forms the moments and shifts them to
-// the splat centre.  The three colour sums take a 4-value transposing butterfly (6 SHFL).  92-98 instead of 111
-// instructions per pair (profiles/r1_sass_blend_bwd.md), at the price of 19 instead of 9 floats of shared memory per
-// (warp, entry) -- hence the CHUNK parameter: 64 entries fit 4 CTAs per SM, 128 entries halve the barriers but leave 2
-// CTAs per SM.  To be timed on the device.
-#define BWH_NVAL 19
 
-template <int CHUNK>
-// 44 KB / 83 KB of shared memory per CTA allow 5 / 2 CTAs per SM; the 64-entry variant is built for 4: squeezing it into
-// 48 registers for 5 costs 23 more instructions per pair (114 vs 91) in rematerialised addresses
-__global__ void __launch_bounds__(BL_THREADS, CHUNK == 64 ? 4 : 2)
-k_blend_bwd_wht(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
-                const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
-                const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
-                const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
+// ---- backward, segment-parallel (default) ------------------------------------------------------------------------
+// One warp = one (tile, segment) unit, all 256 pixels of the tile: lane l owns pixel (l & 7, l >> 3) of each 8x4 block.
+// Per-pixel state, walking back to front:  T = transmittance in front of the current splat,
+//   S = sum over the entries BEHIND it of alpha_j T_j (c_j . dL/dpixel)  +  T_final (bg . dL/dpixel)
+// so that dL/dalpha_k = T_k (c_k . dp) - S_k / (1 - alpha_k) -- the scalar form of the published recurrence
+// (accum_rec / last_alpha, cuda_rasterizer/backward.cu) with the background term folded into the start value.
+#define SG_WARPS 4
+#define SG_THREADS (SG_WARPS * 32)
+#define SG_STAGE 32  // records staged per pass: one per lane
+
+__global__ void __launch_bounds__(SG_THREADS, 6)
+k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
+                const uint2 *__restrict__ ranges, const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
+                const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage, const SegWs seg,
                 float *__restrict__ d_means2D, float *__restrict__ d_conic_opacity, float *__restrict__ d_rgb) {
-    constexpr int STRIDE = CHUNK + 1;
-    extern __shared__ float s_acc[];  // [BL_WARPS][BWH_NVAL][STRIDE]
-    __shared__ SRec s_rec[CHUNK];
-    __shared__ uint32_t s_id[CHUNK];
-    __shared__ uint8_t s_cull[CHUNK];
-    __shared__ uint32_t s_mask[BL_WARPS][CHUNK / 32];
-    __shared__ uint32_t s_max[BL_WARPS];
-    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
-    if (!compute_locally[blockIdx.x]) return;
-    const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
+    __shared__ SRec s_rec_all[SG_WARPS][SG_STAGE];   // c = (green, blue, 1 / opacity, splat id bits)
+    __shared__ float4 s_pix_all[SG_WARPS][8 * 32];   // per pixel: dL/dpixel (3) and the number of live entries (int bits)
+    __shared__ uint32_t s_mask_all[SG_WARPS][SG_STAGE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int px, py;
-    pixel_of_thread(tile, gx, px, py);
-    const bool inside = px < W && py < H;
+    const uint32_t u = blockIdx.x * SG_WARPS + warp;
+    if (u >= *seg.n_units) return;  // warps are independent: no CTA-level synchronisation anywhere below
+    SRec *s_rec = s_rec_all[warp];
+    float4 *s_pix = s_pix_all[warp] + lane;
+    uint32_t *s_mask = s_mask_all[warp];
+    const uint2 unit = seg.units[u];
+    const int tile_g = (int)unit.x, sidx = (int)unit.y;
+    const int view = tile_g / tiles_per_view, tile = tile_g - view * tiles_per_view;
+    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
+    const uint2 range = ranges[tile_g];
+    const int tl = (int)seg.tile_last[tile_g];
+    const int seg_base = sidx * SEG_K;
+    const int cnt = min(SEG_K, tl - seg_base);
     const size_t HW = (size_t)H * W;
-    const size_t pix = (size_t)py * W + px;
     final_T += (size_t)view * HW;
     n_contrib += (size_t)view * HW;
     dL_dimage += (size_t)view * 3 * HW;
-    const uint2 range = ranges[blockIdx.x];
-    const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
-    const float pxf = (float)px, pyf = (float)py;
-    const float T_final = inside ? final_T[pix] : 0.f;
-    const uint32_t last = inside ? n_contrib[pix] : 0u;
-    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
-    if (inside) { dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix]; }
-    const float bgdot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
-    const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
-    // where this lane's Walsh-Hadamard coefficient goes: 0 <- W_0, 1+i <- W_{e_i}, 6+pair(i,j) <- W_{e_i+e_j}
-    int slot = -1;
-    {
-        const int pc = __popc(lane);
-        if (pc == 0) slot = 0;
-        else if (pc == 1) slot = __ffs(lane);  // 1 + bit index
-        else if (pc == 2) {
-            const int i = __ffs(lane) - 1, j = 31 - __clz(lane);
-            slot = 6 + (i * (9 - i)) / 2 + (j - i - 1);
+    const int X0 = (tile % gx) * GS_BLOCK_X, Y0 = (tile / gx) * GS_BLOCK_Y;
+    const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+    const float4 *ck = seg.ckpt + ((size_t)(range.x / SEG_K) + tile_g + sidx) * SEG_SLOT + lane;
+    float T[8], S[8];
+    uint32_t blive = 0, blive_hi = 0;  // byte b: deepest live entry of block b over the warp
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const int px = X0 + (b & 1) * 8 + (lane & 7), py = Y0 + (b >> 1) * 4 + (lane >> 3);
+        const bool inside = px < W && py < H;
+        const size_t pix = (size_t)py * W + px;
+        float Tf = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        int last = 0;
+        if (inside) {
+            Tf = final_T[pix];
+            last = (int)n_contrib[pix];
+            d0 = dL_dimage[pix]; d1 = dL_dimage[HW + pix]; d2 = dL_dimage[2 * HW + pix];
         }
+        const float sbg = Tf * (bg0 * d0 + bg1 * d1 + bg2 * d2);
+        T[b] = Tf;
+        S[b] = sbg;
+        if (last > seg_base + SEG_K) {  // alive beyond this segment: the forward left its state at the boundary
+            const float4 c = ck[b * 32];
+            T[b] = c.x;
+            S[b] = c.y * d0 + c.z * d1 + c.w * d2 + sbg;
+        }
+        const int live = max(0, min(SEG_K, last - seg_base));  // entries [0, live) of the segment are in front of the
+        s_pix[b * 32] = make_float4(d0, d1, d2, __int_as_float(live));  // pixel's last contributor
+        const uint32_t m = __reduce_max_sync(FULL, (uint32_t)live);
+        if (b < 4) blive |= m << (8 * b); else blive_hi |= m << (8 * (b - 4));
     }
-    // sign of this lane in butterfly stage s: -1 if bit s of the lane is set
-    float sg[5];
-#pragma unroll
-    for (int s = 0; s < 5; s++) sg[s] = ((lane >> s) & 1) ? -1.f : 1.f;
-    const bool h16 = lane & 16, h8 = lane & 8;
-    uint32_t m = last;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) s_max[warp] = m;
-    __syncthreads();
-    uint32_t n_total = 0;
-#pragma unroll
-    for (int w = 0; w < BL_WARPS; w++) n_total = max(n_total, s_max[w]);
-    const uint32_t wlast = m;
-    float *acc_w = s_acc + (size_t)warp * BWH_NVAL * STRIDE;
-    // shared-window addresses of this lane's two store rows, formed once (entry j adds 4 j bytes)
-    const uint32_t st_w = gs_smem_u32(acc_w + (slot >= 0 ? slot : 0) * STRIDE);
-    const uint32_t st_q = gs_smem_u32(acc_w + (16 + ((lane >> 3) & 3)) * STRIDE);
-    const bool has_w = slot >= 0, has_q = (lane & 7) == 0 && lane < 24;  // colour totals end in lanes 0, 8, 16
-    float T = T_final, B0 = 0.f, B1 = 0.f, B2 = 0.f;
-    const int n_chunks = ((int)n_total + CHUNK - 1) / CHUNK;
-    for (int c = n_chunks - 1; c >= 0; c--) {
-        const int base = c * CHUNK;
-        const int cnt = min(CHUNK, (int)n_total - base);
-        __syncthreads();  // previous chunk's flush has finished reading shared memory
-        if ((int)threadIdx.x < cnt) {
-            const uint32_t g = ids[range.x + base + threadIdx.x];
-            s_id[threadIdx.x] = g;
+    // lane roles of the final RED: lanes 0,4,...,28 hold sums 0..7 after the butterfly, lane 1 sends sum 8
+    const int role = (lane & 3) == 0 ? (lane >> 2) : (lane == 1 ? 8 : -1);
+    float *rptr = d_means2D;
+    int rstride = 0;
+    float rscale = 0.f;
+    if (role >= 0) {
+        if (role < 2) { rptr = d_means2D + role; rstride = 2; rscale = role == 0 ? 0.5f * (float)W : 0.5f * (float)H; }
+        else if (role < 6) { rptr = d_conic_opacity + (role - 2); rstride = 4; rscale = role == 3 ? -1.f : (role == 5 ? 1.f : -0.5f); }
+        else { rptr = d_rgb + (role - 6); rstride = 3; rscale = 1.f; }
+    }
+    const float pxf0 = (float)(X0 + (lane & 7)), pyf0 = (float)(Y0 + (lane >> 3));
+    for (int pass = (cnt - 1) / SG_STAGE; pass >= 0; pass--) {
+        // stage 32 records, one per lane; entry i keeps only the blocks it can reach (bounding box of {alpha >= 1/255})
+        // that still have a live pixel at depth i
+        const int p0 = pass * SG_STAGE, pn = min(SG_STAGE, cnt - p0);
+        __syncwarp();
+        if (lane < pn) {
+            const int i = p0 + lane;
+            const uint32_t g = ids[range.x + seg_base + i];
             const float4 *r = rec + (size_t)3 * g;
-            const float4 a = __ldg(r), b = __ldg(r + 1), cc = __ldg(r + 2);
-            s_rec[threadIdx.x].a = a; s_rec[threadIdx.x].b = b; s_rec[threadIdx.x].c = cc;
-            s_cull[threadIdx.x] = (uint8_t)block_mask(a.x, a.y, cc.z, cc.w, X0, Y0);
-        }
-        uint32_t wmask = 0u;
-        __syncthreads();
-        if ((uint32_t)base < wlast) {
-            for (int g0 = (cnt - 1) & ~31; g0 >= 0; g0 -= 32) {
-                const int jj = g0 + 31 - lane;
-                uint32_t cand = __ballot_sync(0xffffffffu, jj < cnt && ((s_cull[jj] >> warp) & 1));
-                uint32_t mybits = 0u;
-                const int last_rel = (int)last - base;
-                while (cand) {
-                    const int b31 = 32 - __ffs(cand);
-                    const int j = g0 + b31;
-                    cand &= cand - 1u;
-                    const SRec *sr = &s_rec[j];
-                    const float4 a = sr->a, b = sr->b;
-                    const float dx = a.x - pxf, dy = a.y - pyf;
-                    const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
-                    bool ok = (j < last_rel) && power >= b.z;
-                    if (!__any_sync(0xffffffffu, ok)) continue;
-                    const float G = gs_exp_neg(power);
-                    const float alpha = fminf(ALPHA_MAX, b.y * G);
-                    ok = ok && power <= 0.f && alpha >= ALPHA_MIN;
-                    if (!__any_sync(0xffffffffu, ok)) continue;
-                    const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
-                    const float ae = ok ? alpha : 0.f;
-                    float inv;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - ae));
-                    T = T * inv;
-                    const float d0 = b.w - B0, d1 = gb.x - B1, d2 = gb.y - B2;
-                    const float dL_dalpha = (d0 * dp0 + d1 * dp1 + d2 * dp2) * T - (T_final * inv) * bgdot;
-                    float w = ok ? b.y * dL_dalpha * G : 0.f;   // per-pixel weight m = dL/dG * G
-                    const float dch = ae * T;
-                    B0 += ae * d0; B1 += ae * d1; B2 += ae * d2;
-                    // Walsh-Hadamard butterfly of m over the 32 lanes
+            const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+            uint32_t m = block_mask(a.x, a.y, c.z, c.w, (float)X0, (float)Y0);
 #pragma unroll
-                    for (int s = 0; s < 5; s++) w = __fmaf_rn(sg[s], w, __shfl_xor_sync(0xffffffffu, w, 1 << s));
-                    // colour sums: 4-value transposing butterfly of (c0, c1, c2, 0)
-                    const float c0 = dch * dp0, c1 = dch * dp1, c2 = dch * dp2;
-                    float r0 = (h16 ? c2 : c0) + __shfl_xor_sync(0xffffffffu, h16 ? c0 : c2, 16);
-                    float r1 = (h16 ? 0.f : c1) + __shfl_xor_sync(0xffffffffu, h16 ? c1 : 0.f, 16);
-                    float q = (h8 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, h8 ? r0 : r1, 8);
-                    q += __shfl_xor_sync(0xffffffffu, q, 4);
-                    q += __shfl_xor_sync(0xffffffffu, q, 2);
-                    q += __shfl_xor_sync(0xffffffffu, q, 1);
-                    if (has_w) asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_w + 4u * (uint32_t)j), "f"(w) : "memory");
-                    if (has_q) asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_q + 4u * (uint32_t)j), "f"(q) : "memory");
-                    mybits |= 1u << b31;
-                }
-                if (lane == (g0 >> 5)) wmask = mybits;
+            for (int q = 0; q < 8; q++) {
+                const uint32_t bl = ((q < 4 ? blive : blive_hi) >> (8 * (q & 3))) & 0xffu;
+                if ((uint32_t)i >= bl) m &= ~(1u << q);
             }
-        }
-        if (lane < CHUNK / 32) s_mask[warp][lane] = wmask;
-        __syncthreads();
-        if ((int)threadIdx.x < cnt) {
-            const int j = threadIdx.x;
-            const float4 a = s_rec[j].a, b = s_rec[j].b;
-            float s[9];
-#pragma unroll
-            for (int q = 0; q < 9; q++) s[q] = 0.f;
-            bool any = false;
-#pragma unroll
-            for (int w = 0; w < BL_WARPS; w++) {
-                if ((s_mask[w][j >> 5] >> (j & 31)) & 1u) {
-                    any = true;
-                    const float *cw = s_acc + (size_t)w * BWH_NVAL * STRIDE + j;
-                    float cf[BWH_NVAL];
-#pragma unroll
-                    for (int q = 0; q < BWH_NVAL; q++) cf[q] = cw[q * STRIDE];
-                    // with sum m b_i = (W_0 - E_i)/2 and sum m b_i b_j = (W_0 - E_i - E_j + P_ij)/4 substituted into
-                    // lx = b0 + 2 b1 + 4 b2, ly = b3 + 2 b4 and collected per coefficient
-                    // (E_i = cf[1+i]; P_ij = cf[6 + i(9-i)/2 + j-i-1]: P01 6, P02 7, P03 8, P04 9, P12 10, P13 11, P14 12,
-                    //  P23 13, P24 14, P34 15):
-                    const float W0 = cf[0], E0 = cf[1], E1 = cf[2], E2 = cf[3], E3 = cf[4], E4 = cf[5];
-                    const float Lx = 3.5f * W0 - 0.5f * E0 - E1 - 2.f * E2;                         // sum m lx
-                    const float Ly = 1.5f * W0 - 0.5f * E3 - E4;                                    // sum m ly
-                    const float Lxx = 17.5f * W0 - 3.5f * E0 - 7.f * E1 - 14.f * E2 + cf[6] + 2.f * cf[7] + 4.f * cf[10];
-                    const float Lyy = 3.5f * W0 - 1.5f * E3 - 3.f * E4 + cf[15];
-                    const float Lxy = 0.25f * (21.f * W0 - 3.f * E0 - 6.f * E1 - 12.f * E2 - 7.f * E3 - 14.f * E4 + cf[8] +
-                                               2.f * cf[9] + 2.f * cf[11] + 4.f * cf[12] + 4.f * cf[13] + 8.f * cf[14]);
-                    // offsets of the splat centre from this warp's block origin: dx = ux - lx, dy = uy - ly
-                    const float ux = a.x - (X0 + (float)((w & 1) * 8)), uy = a.y - (Y0 + (float)((w >> 1) * 4));
-                    s[0] += ux * W0 - Lx;
-                    s[1] += uy * W0 - Ly;
-                    s[2] += ux * (ux * W0 - 2.f * Lx) + Lxx;
-                    s[3] += ux * (uy * W0 - Ly) - uy * Lx + Lxy;
-                    s[4] += uy * (uy * W0 - 2.f * Ly) + Lyy;
-                    s[5] += W0;
-                    s[6] += cf[16]; s[7] += cf[17]; s[8] += cf[18];
-                }
-            }
-            if (any) {
-                const uint32_t g = s_id[j];
-                atomicAdd(d_means2D + 2 * (size_t)g, (2.f * a.z * s[0] + a.w * s[1]) * ddelx_dx);
-                atomicAdd(d_means2D + 2 * (size_t)g + 1, (2.f * b.x * s[1] + a.w * s[0]) * ddely_dy);
-                atomicAdd(d_conic_opacity + 4 * (size_t)g, -0.5f * s[2]);
-                atomicAdd(d_conic_opacity + 4 * (size_t)g + 1, -s[3]);
-                atomicAdd(d_conic_opacity + 4 * (size_t)g + 2, -0.5f * s[4]);
-                atomicAdd(d_conic_opacity + 4 * (size_t)g + 3, __fdividef(s[5], b.y));
-                atomicAdd(d_rgb + 3 * (size_t)g, s[6]);
-                atomicAdd(d_rgb + 3 * (size_t)g + 1, s[7]);
-                atomicAdd(d_rgb + 3 * (size_t)g + 2, s[8]);
-            }
-        }
-    }
-}
-
-template <int CHUNK>
-static int launch_bwd_wht(int grid, cudaStream_t stream, int W, int H, int T1, const float4 *rec, const float *bg,
-                          const uint8_t *cl, const uint2 *ranges, const uint32_t *ids, const float *final_T,
-                          const uint32_t *n_contrib, const float *dimg, float *d_m2, float *d_co, float *d_rgb) {
-    const size_t dyn = sizeof(float) * BL_WARPS * BWH_NVAL * (CHUNK + 1);
-    GS_CUDA_TRY(cudaFuncSetAttribute(k_blend_bwd_wht<CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    k_blend_bwd_wht<CHUNK><<<grid, BL_THREADS, dyn, stream>>>(W, H, T1, rec, bg, cl, ranges, ids, final_T, n_contrib, dimg,
-                                                              d_m2, d_co, d_rgb);
-    GS_LAUNCH_CHECK();
-    return GS_OK;
-}
-
-// ---- backward, EXPERIMENTAL variant 2 (off by default; gs_debug_set(GS_DEBUG_BWD_AUTO)) ---------------------------
-// "Warp-autonomous": no CTA barrier and no shared partial-sum slots at all.  Every warp walks the tile's list on its
-// own for its two 4x4 pixel blocks (one per half-warp, the forward's layout: ~60 % useful lanes instead of 37 %), 32
-// entries at a time: lane l loads entry l's record into a warp-private staging row and computes its block mask, two
-// ballots give each half-warp its candidates, and each candidate pair is reduced over the 16 lanes of its half (9-value
-// transposing butterfly, 12 SHFL for BOTH halves together) and leaves the SM at once as ONE predicated RED.ADD
-// instruction: the lane pair that ends up holding a sum adds "its" terms of the gradient (even lane / odd lane take
-// the two outputs a sum feeds -- e.g. sum(m dx) feeds dL/dmean_x with 2a' and dL/dmean_y with b').  That is 11 global
-// atomics per (4x4 block, splat) instead of 9 per (tile, splat), in exchange for: no flush pass, no barrier stalls (the
-// default kernel idles ~20 % of its issue slots waiting at 3 barriers per chunk), and ~75 instead of 110 issued
-// instructions per 8x4-block-equivalent pair.  Records are re-read by all 8 warps of a tile (L1 hits).  Whether the
-// L2 atomic units keep up (~1.8e8 RED per c2 backward) is what the device run has to tell.
-GS_D void half_reduce9(float v[9], int l16) {
-    {
-        const bool h = l16 & 8;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float send = h ? v[i] : v[i + 4], keep = h ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool h = l16 & 4;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const float send = h ? v[i] : v[i + 2], keep = h ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    {
-        const bool h = l16 & 2;
-        const float send = h ? v[0] : v[1], keep = h ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);  // lanes 2q, 2q+1 of the half: total of value q
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v[8] += __shfl_xor_sync(0xffffffffu, v[8], o);
-}
-
-__global__ void __launch_bounds__(BL_THREADS)
-k_blend_bwd_auto(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
-                 const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
-                 const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
-                 const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
-                 float *__restrict__ d_means2D, float *__restrict__ d_conic_opacity, float *__restrict__ d_rgb) {
-    __shared__ SRec s_stage[BL_WARPS][32];
-    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
-    if (!compute_locally[blockIdx.x]) return;
-    const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Where me = where_am_i(tile, gx);
-    const int px = me.px, py = me.py, l16 = me.l16;
-    const bool inside = px < W && py < H;
-    const size_t HW = (size_t)H * W;
-    const size_t pix = (size_t)py * W + px;
-    final_T += (size_t)view * HW;
-    n_contrib += (size_t)view * HW;
-    dL_dimage += (size_t)view * 3 * HW;
-    const uint2 range = ranges[blockIdx.x];
-    const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
-    const float pxf = (float)px, pyf = (float)py;
-    const float T_final = inside ? final_T[pix] : 0.f;
-    const int last = inside ? (int)n_contrib[pix] : 0;
-    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
-    if (inside) { dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix]; }
-    const float bgdot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
-    const float ddx = 0.5f * (float)W, ddy = 0.5f * (float)H;  // dL/dmeans2D is per NDC unit
-    // What this lane adds after the reduction (it holds the sum with index (l16 >> 1) & 7; odd lanes take the second
-    // output of that sum): target array, element, and the coefficient  kA a' + kB b' + kC c' + kK + kO / opacity.
-    float kA = 0.f, kB = 0.f, kC = 0.f, kK = 0.f, kO = 0.f;
-    float *out = nullptr;
-    int stride = 0;
-    switch (l16) {
-        case 0: out = d_means2D; stride = 2; kA = 2.f * ddx; break;            // sum m dx   -> mean_x
-        case 1: out = d_means2D + 1; stride = 2; kB = ddy; break;              // sum m dx   -> mean_y
-        case 2: out = d_means2D; stride = 2; kB = ddx; break;                  // sum m dy   -> mean_x
-        case 3: out = d_means2D + 1; stride = 2; kC = 2.f * ddy; break;        // sum m dy   -> mean_y
-        case 4: out = d_conic_opacity; stride = 4; kK = -0.5f; break;          // sum m dx^2
-        case 5: out = d_rgb + 2; stride = 3; kK = 1.f; break;                  // blue (value 8, held by every lane)
-        case 6: out = d_conic_opacity + 1; stride = 4; kK = -1.f; break;       // sum m dx dy
-        case 8: out = d_conic_opacity + 2; stride = 4; kK = -0.5f; break;      // sum m dy^2
-        case 10: out = d_conic_opacity + 3; stride = 4; kO = 1.f; break;       // sum m      -> opacity
-        case 12: out = d_rgb; stride = 3; kK = 1.f; break;                     // red
-        case 14: out = d_rgb + 1; stride = 3; kK = 1.f; break;                 // green
-        default: break;
-    }
-    const bool takes_v8 = l16 == 5;
-    const uint32_t stride4 = 4u * (uint32_t)stride;  // bytes between the target elements of consecutive splats
-    uint32_t m = (uint32_t)last;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const int wlast = (int)m;  // deepest entry any pixel of this warp reaches
-    const int blkA = me.blk - me.half;
-    const uint32_t half_lanes = me.half ? 0xffff0000u : 0x0000ffffu;
-    SRec *stage = s_stage[warp];
-    float T = T_final, B0 = 0.f, B1 = 0.f, B2 = 0.f;
-    for (int g0 = (wlast - 1) & ~31; g0 >= 0 && wlast > 0; g0 -= 32) {
-        // stage entries g0 .. g0+31 (lane l <- entry g0 + l)
-        const int e = g0 + lane;
-        uint32_t gid = 0u, m16 = 0u;
-        __syncwarp();  // the previous batch's reads of the staging row are done
-        if (e < wlast) {
-            gid = ids[range.x + e];
-            const float4 *r = rec + (size_t)3 * gid;
-            const float4 a = __ldg(r), b = __ldg(r + 1), cc = __ldg(r + 2);
-            stage[lane].a = a; stage[lane].b = b; stage[lane].c = cc;
-            m16 = block_mask16(a.x, a.y, cc.z, cc.w, X0, Y0);
+            s_rec[lane].a = a; s_rec[lane].b = b;
+            s_rec[lane].c = make_float4(c.x, c.y, __frcp_rn(b.y), __uint_as_float(g));
+            s_mask[lane] = m;
         }
         __syncwarp();
-        const uint32_t cA = __ballot_sync(0xffffffffu, (m16 >> blkA) & 1u),
-                       cB = __ballot_sync(0xffffffffu, (m16 >> (blkA + 1)) & 1u);
-        uint32_t mine = me.half ? cB : cA;  // this half-warp's candidates; bit l <-> entry g0 + l
-        const int last_rel = last - g0;     // entry g0 + j is live for this pixel iff j < last_rel
-        while (__any_sync(0xffffffffu, mine != 0u)) {
-            const bool has = mine != 0u;
-            const int j = has ? 31 - __clz(mine) : 0;  // deepest remaining candidate of this half
-            mine &= ~(1u << j);                         // (no-op when !has: mine == 0)
-            const SRec *sr = &stage[j];
-            const float4 a = sr->a, b = sr->b;
-            const float dx = a.x - pxf, dy = a.y - pyf;
-            const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
-            bool ok = (has & (j < last_rel)) & (power >= b.z);   // '&': evaluate everything once, no short circuit
-            if (!__any_sync(0xffffffffu, ok)) continue;
-            const float G = gs_exp_neg(power);
-            const float alpha = fminf(ALPHA_MAX, b.y * G);
-            ok = ok & (power <= 0.f) & (alpha >= ALPHA_MIN);
-            const uint32_t okb = __ballot_sync(0xffffffffu, ok);
-            if (okb == 0u) continue;
+        for (int jl = pn - 1; jl >= 0; jl--) {
+            // warp-uniform by construction; the redux makes that visible to the compiler (uniform branches, no
+            // reconvergence bookkeeping around the votes below)
+            const uint32_t m8 = __reduce_or_sync(FULL, s_mask[jl]);
+            if (m8 == 0u) continue;
+            const int j = p0 + jl;
+            const float4 a = s_rec[jl].a, b4 = s_rec[jl].b, c4 = s_rec[jl].c;
+            const float mxl = a.x - pxf0, myl = a.y - pyf0;
             float v[9];
-            {
-                const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
-                const float ae = ok ? alpha : 0.f;
-                float inv;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - ae));
-                T = T * inv;
-                const float d0 = b.w - B0, d1 = gb.x - B1, d2 = gb.y - B2;
-                const float dL_dalpha = (d0 * dp0 + d1 * dp1 + d2 * dp2) * T - (T_final * inv) * bgdot;
-                const float mw = ok ? b.y * dL_dalpha * G : 0.f;
-                const float dch = ae * T;
-                B0 += ae * d0; B1 += ae * d1; B2 += ae * d2;
-                const float mx_ = mw * dx, my_ = mw * dy;
-                v[0] = mx_; v[1] = my_; v[2] = mx_ * dx; v[3] = mx_ * dy; v[4] = my_ * dy; v[5] = mw;
-                v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
+#pragma unroll
+            for (int q = 0; q < 9; q++) v[q] = 0.f;
+            bool any_full = false;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                if (m8 & (1u << b)) {
+                    const float4 pc = s_pix[b * 32];
+                    const float dx = mxl - (float)((b & 1) * 8), dy = myl - (float)((b >> 1) * 4);
+                    const float power = dx * (a.z * dx + a.w * dy) + b4.x * dy * dy;
+                    const bool ok1 = (j < __float_as_int(pc.w)) && power >= b4.z && power <= 0.f;
+                    if (__any_sync(FULL, ok1)) {
+                        const float G = gs_exp_neg(power);
+                        const float alpha = fminf(ALPHA_MAX, b4.y * G);
+                        const bool ok = ok1 && alpha >= ALPHA_MIN;
+                        const float ae = ok ? alpha : 0.f;   // effective alpha: 0 = this lane skips the splat
+                        float inv;                            // 1/(1-ae), 1-ae in [0.01, 1]: one MUFU.RCP
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - ae));
+                        const float Tk = T[b] * inv;          // transmittance in front of this splat
+                        T[b] = Tk;
+                        const float cd = b4.w * pc.x + c4.x * pc.y + c4.y * pc.z;
+                        const float dL_dalpha = cd * Tk - S[b] * inv;
+                        const float mw = ok ? b4.y * dL_dalpha * G : 0.f;
+                        const float dch = ae * Tk;
+                        S[b] += dch * cd;
+                        const float mx_ = mw * dx, my_ = mw * dy;
+                        v[0] += mx_; v[1] += my_; v[2] += mx_ * dx; v[3] += mx_ * dy; v[4] += my_ * dy; v[5] += mw;
+                        v[6] += dch * pc.x; v[7] += dch * pc.y; v[8] += dch * pc.z;
+                        any_full = true;
+                    }
+                }
             }
-            half_reduce9(v, l16);
-            const uint32_t g = __shfl_sync(0xffffffffu, gid, j);  // splat id of this half's entry
-            if (out != nullptr && (okb & half_lanes) != 0u) {
-                float inv_o;  // opacity >= 1/255 here (alpha >= 1/255 was reached): no denormal handling needed
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_o) : "f"(b.y));
-                const float coef = kA * a.z + kB * a.w + kC * b.x + kK + kO * inv_o;
-                float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + (size_t)g * stride4);
-                atomicAdd(dst, coef * (takes_v8 ? v[8] : v[0]));
+            if (!any_full) continue;
+            {   // per-lane pre-mix (linear, commutes with the sums), so that every reduced value is ONE output element:
+                // d power/d mean = (2a'dx + b'dy, 2c'dy + b'dx); dL/dopacity = sum(m) / opacity
+                const float sx = v[0], sy = v[1];
+                v[0] = 2.f * a.z * sx + a.w * sy;
+                v[1] = 2.f * b4.x * sy + a.w * sx;
+                v[5] *= c4.z;
             }
+            warp_reduce9(v, lane);
+            const float val = (lane == 1 ? v[8] : v[0]) * rscale;
+            if (role >= 0) atomicAdd(rptr + (size_t)__float_as_uint(c4.w) * rstride, val);
         }
     }
+}
+
+template <bool STATS, bool CKPT>
+static void launch_fwd(int grid, cudaStream_t stream, int W, int H, int T1, const float *rec, const float *bg,
+                       const uint8_t *cl, const uint32_t *ranges, const uint32_t *ids, float *image, float *final_T,
+                       uint32_t *n_contrib, int64_t *stats, const SegWs &seg) {
+    k_blend_fwd<STATS, CKPT><<<grid, BL_THREADS, 0, stream>>>(
+        W, H, T1, reinterpret_cast<const float4 *>(rec), bg, cl, reinterpret_cast<const uint2 *>(ranges), ids, image,
+        final_T, n_contrib, reinterpret_cast<unsigned long long *>(stats), seg);
 }
 
 int gs_launch_blend_forward(int num_views, int64_t R, int H, int W, const float *rec, const float *bg,
                             const uint8_t *compute_locally, const uint32_t *ranges, const uint32_t *ids_sorted,
-                            float *image, float *final_T, uint32_t *n_contrib, int64_t *stats, cudaStream_t stream) {
-    (void)R;
+                            float *image, float *final_T, uint32_t *n_contrib, int64_t *stats, void *seg_ws,
+                            size_t seg_ws_bytes, cudaStream_t stream) {
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     const int T1 = gx * gy;
+    SegWs seg = {nullptr, nullptr, nullptr, nullptr};
+    if (seg_ws) {
+        if (seg_ws_bytes < seg_bytes(R, (int64_t)T1 * num_views)) {
+            gs_set_error("gs_render_forward: segment workspace too small (%zu < %zu)", seg_ws_bytes,
+                         seg_bytes(R, (int64_t)T1 * num_views));
+            return GS_ENOMEM;
+        }
+        GS_REQUIRE(((uintptr_t)seg_ws & 255) == 0, "segment workspace must be 256-byte aligned");
+        seg = seg_carve(seg_ws, R, (int64_t)T1 * num_views);
+        GS_CUDA_TRY(cudaMemsetAsync(seg.n_units, 0, 256, stream));
+    }
     if (stats) GS_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t) * (size_t)num_views, stream));
     GsStageTimer timer(GS_STAGE_BLEND_FWD, stream);
-    auto *st = reinterpret_cast<unsigned long long *>(stats);
-    if (stats)
-        k_blend_fwd<true><<<T1 * num_views, BL_THREADS, 0, stream>>>(
-            W, H, T1, reinterpret_cast<const float4 *>(rec), bg, compute_locally, reinterpret_cast<const uint2 *>(ranges),
-            ids_sorted, image, final_T, n_contrib, st);
+    const int grid = T1 * num_views;
+    if (stats && seg_ws)
+        launch_fwd<true, true>(grid, stream, W, H, T1, rec, bg, compute_locally, ranges, ids_sorted, image, final_T, n_contrib, stats, seg);
+    else if (stats)
+        launch_fwd<true, false>(grid, stream, W, H, T1, rec, bg, compute_locally, ranges, ids_sorted, image, final_T, n_contrib, stats, seg);
+    else if (seg_ws)
+        launch_fwd<false, true>(grid, stream, W, H, T1, rec, bg, compute_locally, ranges, ids_sorted, image, final_T, n_contrib, stats, seg);
     else
-        k_blend_fwd<false><<<T1 * num_views, BL_THREADS, 0, stream>>>(
-            W, H, T1, reinterpret_cast<const float4 *>(rec), bg, compute_locally, reinterpret_cast<const uint2 *>(ranges),
-            ids_sorted, image, final_T, n_contrib, st);
+        launch_fwd<false, false>(grid, stream, W, H, T1, rec, bg, compute_locally, ranges, ids_sorted, image, final_T, n_contrib, stats, seg);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
@@ -778,17 +666,19 @@ int gs_launch_blend_forward(int num_views, int64_t R, int H, int W, const float 
 extern "C" int gs_render_backward(int P, int64_t R, int image_height, int image_width, const float *rec,
                                   const float *bg, const uint8_t *compute_locally, const uint32_t *ranges,
                                   const uint32_t *ids_sorted, const float *final_T, const uint32_t *n_contrib,
-                                  const float *dL_dimage, float *dL_dmeans2D, float *dL_dconic_opacity, float *dL_drgb,
-                                  void *stream) {
+                                  const float *dL_dimage, const void *seg_ws, size_t seg_ws_bytes, float *dL_dmeans2D,
+                                  float *dL_dconic_opacity, float *dL_drgb, void *stream) {
     return gs_render_backward_batched(1, P, R, image_height, image_width, rec, bg, compute_locally, ranges, ids_sorted,
-                                      final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity, dL_drgb, stream);
+                                      final_T, n_contrib, dL_dimage, seg_ws, seg_ws_bytes, dL_dmeans2D, dL_dconic_opacity,
+                                      dL_drgb, stream);
 }
 
 extern "C" int gs_render_backward_batched(int num_views, int P, int64_t R, int image_height, int image_width,
                                           const float *rec, const float *bg, const uint8_t *compute_locally,
                                           const uint32_t *ranges, const uint32_t *ids_sorted, const float *final_T,
-                                          const uint32_t *n_contrib, const float *dL_dimage, float *dL_dmeans2D,
-                                          float *dL_dconic_opacity, float *dL_drgb, void *stream_) {
+                                          const uint32_t *n_contrib, const float *dL_dimage, const void *seg_ws,
+                                          size_t seg_ws_bytes, float *dL_dmeans2D, float *dL_dconic_opacity,
+                                          float *dL_drgb, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GS_REQUIRE(num_views >= 1 && num_views <= GS_MAX_VIEWS, "num_views must be in [1, GS_MAX_VIEWS]");
     GS_REQUIRE(P >= 0 && R >= 0 && image_height > 0 && image_width > 0, "sizes");
@@ -801,22 +691,20 @@ extern "C" int gs_render_backward_batched(int num_views, int P, int64_t R, int i
     GS_REQUIRE(rec && bg && compute_locally && ranges && ids_sorted && final_T && n_contrib && dL_dimage, "null input");
     const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     GsStageTimer timer(GS_STAGE_BLEND_BWD, stream);
-    if (g_gs_debug_flags & (GS_DEBUG_BWD_WHT_64 | GS_DEBUG_BWD_WHT_128 | GS_DEBUG_BWD_AUTO)) {  // experimental, see above
-        const float4 *r4 = reinterpret_cast<const float4 *>(rec);
-        const uint2 *rg = reinterpret_cast<const uint2 *>(ranges);
-        if (g_gs_debug_flags & GS_DEBUG_BWD_AUTO) {
-            k_blend_bwd_auto<<<gx * gy * num_views, BL_THREADS, 0, stream>>>(
-                image_width, image_height, gx * gy, r4, bg, compute_locally, rg, ids_sorted, final_T, n_contrib, dL_dimage,
-                dL_dmeans2D, dL_dconic_opacity, dL_drgb);
-            GS_LAUNCH_CHECK();
-            return GS_OK;
+    if (seg_ws && !(g_gs_debug_flags & GS_DEBUG_BWD_TILE)) {
+        const int64_t T = (int64_t)gx * gy * num_views;
+        if (seg_ws_bytes < seg_bytes(R, T)) {
+            gs_set_error("gs_render_backward: segment workspace too small");
+            return GS_ENOMEM;
         }
-        if (g_gs_debug_flags & GS_DEBUG_BWD_WHT_64)
-            return launch_bwd_wht<64>(gx * gy * num_views, stream, image_width, image_height, gx * gy, r4, bg,
-                                      compute_locally, rg, ids_sorted, final_T, n_contrib, dL_dimage, dL_dmeans2D,
-                                      dL_dconic_opacity, dL_drgb);
-        return launch_bwd_wht<128>(gx * gy * num_views, stream, image_width, image_height, gx * gy, r4, bg, compute_locally,
-                                   rg, ids_sorted, final_T, n_contrib, dL_dimage, dL_dmeans2D, dL_dconic_opacity, dL_drgb);
+        const SegWs seg = seg_carve(const_cast<void *>(seg_ws), R, T);
+        const int64_t max_units = R / SEG_K + T;   // >= sum over tiles of ceil(walked entries / SEG_K)
+        k_blend_bwd_seg<<<(unsigned)((max_units + SG_WARPS - 1) / SG_WARPS), SG_THREADS, 0, stream>>>(
+            image_width, image_height, gx * gy, reinterpret_cast<const float4 *>(rec), bg,
+            reinterpret_cast<const uint2 *>(ranges), ids_sorted, final_T, n_contrib, dL_dimage, seg, dL_dmeans2D,
+            dL_dconic_opacity, dL_drgb);
+        GS_LAUNCH_CHECK();
+        return GS_OK;
     }
     k_blend_bwd<<<gx * gy * num_views, BL_THREADS, 0, stream>>>(
         image_width, image_height, gx * gy, reinterpret_cast<const float4 *>(rec), bg, compute_locally,

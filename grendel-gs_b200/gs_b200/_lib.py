@@ -35,14 +35,16 @@ SIGNATURES = {
     "gs_render_count_temp_bytes": (_sz, [_i]),
     "gs_render_count": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
     "gs_render_sort_temp_bytes": (_sz, [_i64]),
+    "gs_render_seg_bytes": (_sz, [_i64, _i]),
     "gs_render_forward": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
-                               _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gs_render_backward": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                               _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gs_render_backward": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "gs_render_count_batched": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                      C.POINTER(_i64), _vp]),
     "gs_render_forward_batched": (_i, [_i, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                       _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gs_render_backward_batched": (_i, [_i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                       _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gs_render_backward_batched": (_i, [_i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,
+                                        _vp, _vp]),
     "gs_loss_temp_bytes_batched": (_sz, [_i, _vp, _i]),
     "gs_loss_forward_batched": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gs_loss_backward_batched": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -126,9 +128,7 @@ def ptr(t):
 
 STAGE_NUM = 14
 DEBUG_NO_BLOCK_CULL = 1
-DEBUG_BWD_WHT_64 = 2     # experimental backward kernels (include/grendel_gs_b200.h), off by default
-DEBUG_BWD_WHT_128 = 4
-DEBUG_BWD_AUTO = 8
+DEBUG_BWD_TILE = 2       # gs_render_backward: round 1's tile-parallel kernel instead of the segment-parallel one
 
 
 def debug_set(flags):

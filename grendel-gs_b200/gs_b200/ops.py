@@ -218,6 +218,14 @@ def _tiles(rs):
     return (int(rs.image_height) + BLOCK_Y - 1) // BLOCK_Y, (int(rs.image_width) + BLOCK_X - 1) // BLOCK_X
 
 
+def _seg_workspace(R, num_tiles, dev, needed):
+    """Segment workspace linking a render forward to its backward (gs_render_seg_bytes); None for forward-only calls."""
+    if not needed or R == 0:
+        return None, 0
+    nb = _lib.query("gs_render_seg_bytes", R, num_tiles)
+    return torch.empty((nb,), dtype=torch.uint8, device=dev), nb
+
+
 class _RenderGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2D, conic_opacity, rgb, depths, radii, compute_locally, rs, collector):
@@ -264,14 +272,15 @@ class _RenderGaussians(torch.autograd.Function):
         final_T = torch.empty((H, W), dtype=torch.float32, device=dev)
         n_contrib = torch.empty((H, W), dtype=torch.int32, device=dev)
         stats = torch.empty((3,), dtype=torch.int64, device=dev)
+        seg, segb = _seg_workspace(R, T, dev, means2D.requires_grad or conic_opacity.requires_grad or rgb.requires_grad)
         _lib.call("gs_render_forward", P, R, H, W, means2D.data_ptr(), radii.data_ptr(), cl.data_ptr(),
                   order.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), tiles[0].data_ptr(),
                   ids[0].data_ptr(), tiles[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(),
-                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), s)
+                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), _lib.ptr(seg), segb, s)
         ev1.record()
         _timed(collector, "forward_render_time", ev0, ev1)
         ids_sorted = ids[1].clone() if R > 0 else ids[1]  # let the 2R-entry scratch go back to the allocator
-        ctx.rs, ctx.R, ctx.P, ctx.collector = rs, R, P, collector
+        ctx.rs, ctx.R, ctx.P, ctx.collector, ctx.seg = rs, R, P, collector, seg
         ctx.save_for_backward(rec, bg, cl, ranges, ids_sorted, final_T, n_contrib)
         n_render, n_consider, n_contrib_sum = stats[0], stats[1], stats[2]
         ctx.mark_non_differentiable(n_render, n_consider, n_contrib_sum)
@@ -289,9 +298,12 @@ class _RenderGaussians(torch.autograd.Function):
         d_rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        seg = ctx.seg
         _lib.call("gs_render_backward", P, R, H, W, rec.data_ptr(), bg.data_ptr(), cl.data_ptr(), ranges.data_ptr(),
                   ids_sorted.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), g_image.data_ptr(),
+                  _lib.ptr(seg), 0 if seg is None else seg.numel(),
                   d_means2D.data_ptr(), d_conic.data_ptr(), d_rgb.data_ptr(), _stream())
+        ctx.seg = None
         ev1.record()
         _timed(ctx.collector, "backward_render_time", ev0, ev1)
         return d_means2D, d_conic, d_rgb, None, None, None, None, None
@@ -368,14 +380,15 @@ class _RenderGaussiansBatched(torch.autograd.Function):
         final_T = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         n_contrib = torch.empty((B, H, W), dtype=torch.int32, device=dev)
         stats = torch.empty((B, 3), dtype=torch.int64, device=dev)
+        seg, segb = _seg_workspace(R, B * T, dev, means2D.requires_grad or conic_opacity.requires_grad or rgb.requires_grad)
         _lib.call("gs_render_forward_batched", B, vs, R, H, W, means2D.data_ptr(), radii.data_ptr(), cl.data_ptr(),
                   order.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), tiles[0].data_ptr(),
                   ids[0].data_ptr(), tiles[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(),
-                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), s)
+                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), _lib.ptr(seg), segb, s)
         ev1.record()
         _timed(collector, "forward_render_time", ev0, ev1)
         ids_sorted = ids[1].clone() if R > 0 else ids[1]  # let the 2R-entry scratch go back to the allocator
-        ctx.rs, ctx.R, ctx.P, ctx.B, ctx.collector = rs, R, P, B, collector
+        ctx.rs, ctx.R, ctx.P, ctx.B, ctx.collector, ctx.seg = rs, R, P, B, collector, seg
         ctx.save_for_backward(rec, bg, cl, ranges, ids_sorted, final_T, n_contrib)
         ctx.mark_non_differentiable(stats)
         return image, stats
@@ -392,9 +405,12 @@ class _RenderGaussiansBatched(torch.autograd.Function):
         d_rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        seg = ctx.seg
         _lib.call("gs_render_backward_batched", B, P, R, H, W, rec.data_ptr(), bg.data_ptr(), cl.data_ptr(),
                   ranges.data_ptr(), ids_sorted.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), g_image.data_ptr(),
+                  _lib.ptr(seg), 0 if seg is None else seg.numel(),
                   d_means2D.data_ptr(), d_conic.data_ptr(), d_rgb.data_ptr(), _stream())
+        ctx.seg = None
         ev1.record()
         _timed(ctx.collector, "backward_render_time", ev0, ev1)
         return d_means2D, d_conic, d_rgb, None, None, None, None, None, None

@@ -158,23 +158,32 @@ GS_API int gs_render_count(int P, int image_height, int image_width, const float
 /* Bytes of radix-sort scratch for R instances. */
 GS_API size_t gs_render_sort_temp_bytes(int64_t R);
 
+/* Bytes of the segment workspace that links a forward to its backward (R instances, num_tiles = tiles of all views):
+ * the forward leaves a per-pixel checkpoint every 64 entries of a tile list plus the list of (tile, segment) units,
+ * which lets gs_render_backward walk every segment independently (csrc/blend.cu, k_blend_bwd_seg).  No reference
+ * counterpart: the published backward re-walks each tile list as a whole (cuda_rasterizer/backward.cu). */
+GS_API size_t gs_render_seg_bytes(int64_t R, int num_tiles);
+
 /* tiles_unsorted/tiles_sorted: (R) uint32 tile ids; ids_unsorted/ids_sorted: (R) uint32 splat ids.
  * ranges: (T,2) uint32 [start,end) per tile.  bg: (3).  image: (3,H,W) -- written in full: non-local
  * tiles are exactly 0 (loss_distribution.py:1875).  final_T (H,W) f32 and n_contrib (H,W) uint32 are
- * kept for the backward.  stats: optional (3) int64 sums of n_render / n_consider / n_contrib, or NULL. */
+ * kept for the backward.  stats: optional (3) int64 sums of n_render / n_consider / n_contrib, or NULL.
+ * seg_ws: gs_render_seg_bytes(R, T) bytes, 256-byte aligned, kept for the backward; NULL for a forward-only render
+ * (mode "test", gaussian_renderer/__init__.py:524: no checkpoints are written; the image is bit-identical). */
 GS_API int gs_render_forward(int P, int64_t R, int image_height, int image_width, const float *means2D,
                              const int32_t *radii, const uint8_t *compute_locally, const uint32_t *order,
                              const uint32_t *offsets, const float *rec, const float *bg, uint32_t *tiles_unsorted,
                              uint32_t *ids_unsorted, uint32_t *tiles_sorted, uint32_t *ids_sorted, void *sort_temp,
                              size_t sort_temp_bytes, uint32_t *ranges, float *image, float *final_T,
-                             uint32_t *n_contrib, int64_t *stats, void *stream);
+                             uint32_t *n_contrib, int64_t *stats, void *seg_ws, size_t seg_ws_bytes, void *stream);
 
 /* dL_dimage: (3,H,W).  The three gradient outputs (P,2) (P,4) (P,3) are zero-filled and
- * accumulated by this call. */
+ * accumulated by this call.  seg_ws: the workspace the forward filled (segment-parallel kernel), or NULL (tile-parallel
+ * kernel of round 1: one CTA per tile; same results up to summation order). */
 GS_API int gs_render_backward(int P, int64_t R, int image_height, int image_width, const float *rec, const float *bg,
                        const uint8_t *compute_locally, const uint32_t *ranges, const uint32_t *ids_sorted,
-                       const float *final_T, const uint32_t *n_contrib, const float *dL_dimage, float *dL_dmeans2D,
-                       float *dL_dconic_opacity, float *dL_drgb, void *stream);
+                       const float *final_T, const uint32_t *n_contrib, const float *dL_dimage, const void *seg_ws,
+                       size_t seg_ws_bytes, float *dL_dmeans2D, float *dL_dconic_opacity, float *dL_drgb, void *stream);
 
 /* ---- the same three calls for ALL cameras of a training batch at once --------------------------------------
  * The reference loops over the B cameras of a batch and calls render_gaussians once per camera
@@ -201,12 +210,14 @@ GS_API int gs_render_forward_batched(int num_views, const int32_t *view_start_ho
                                      const float *rec, const float *bg, uint32_t *tiles_unsorted, uint32_t *ids_unsorted,
                                      uint32_t *tiles_sorted, uint32_t *ids_sorted, void *sort_temp,
                                      size_t sort_temp_bytes, uint32_t *ranges, float *image, float *final_T,
-                                     uint32_t *n_contrib, int64_t *stats, void *stream);
+                                     uint32_t *n_contrib, int64_t *stats, void *seg_ws, size_t seg_ws_bytes,
+                                     void *stream);
 GS_API int gs_render_backward_batched(int num_views, int P, int64_t R, int image_height, int image_width,
                                       const float *rec, const float *bg, const uint8_t *compute_locally,
                                       const uint32_t *ranges, const uint32_t *ids_sorted, const float *final_T,
-                                      const uint32_t *n_contrib, const float *dL_dimage, float *dL_dmeans2D,
-                                      float *dL_dconic_opacity, float *dL_drgb, void *stream);
+                                      const uint32_t *n_contrib, const float *dL_dimage, const void *seg_ws,
+                                      size_t seg_ws_bytes, float *dL_dmeans2D, float *dL_dconic_opacity, float *dL_drgb,
+                                      void *stream);
 
 /* ---- per-kernel device timing ------------------------------------------------------------------
  * The reference's fork logs per-stage GPU times under --zhx_time ("10 preprocess time: 0.29 ms", ...;
@@ -242,15 +253,9 @@ GS_API const char *gs_profile_stage_name(int stage);
  * unculled kernels produce the same image and n_contrib.  Returns the previous flags. */
 enum {
     GS_DEBUG_NO_BLOCK_CULL = 1,
-    /* EXPERIMENTAL, off by default: gs_render_backward with the Walsh-Hadamard moment reduction (csrc/blend.cu,
-     * k_blend_bwd_wht), 64- or 128-entry chunks; same inputs and outputs.  Written after round 1's GPU budget was
-     * spent: to be validated (tests/test_gpu_parity.py, GS_B200_EXPERIMENTAL=1) and timed before it may become the
-     * default. */
-    GS_DEBUG_BWD_WHT_64 = 2,
-    GS_DEBUG_BWD_WHT_128 = 4,
-    /* EXPERIMENTAL, same status: warp-autonomous gs_render_backward (k_blend_bwd_auto): no CTA barriers, 4x4 blocks per
-     * half-warp, per-(block, splat) global atomics. */
-    GS_DEBUG_BWD_AUTO = 8
+    /* gs_render_backward: use the tile-parallel kernel of round 1 (one CTA per tile, k_blend_bwd) even when a segment
+     * workspace is passed -- A/B timing and cross-checking of the two backward kernels. */
+    GS_DEBUG_BWD_TILE = 2
 };
 GS_API int gs_debug_set(int flags);
 

@@ -58,8 +58,9 @@ def preprocess_backward(d, c, cam, pre, g_means2D, g_conic, g_rgb, scale_modifie
     return out
 
 
-def render_forward(H, W, means2D, conic_opacity, rgb, depths, radii, compute_locally, bg):
-    """All tensors on the device. Returns a dict holding every intermediate of the binning + blend."""
+def render_forward(H, W, means2D, conic_opacity, rgb, depths, radii, compute_locally, bg, seg=True):
+    """All tensors on the device. Returns a dict holding every intermediate of the binning + blend.
+    seg=False: forward-only call (no segment workspace; a backward then runs the tile-parallel kernel)."""
     P = means2D.shape[0]
     T = ((H + 15) // 16) * ((W + 15) // 16)
     cl = compute_locally.to(torch.uint8).contiguous()
@@ -84,17 +85,21 @@ def render_forward(H, W, means2D, conic_opacity, rgb, depths, radii, compute_loc
     final_T = torch.zeros((H, W), device=DEV)
     n_contrib = torch.zeros((H, W), dtype=torch.int32, device=DEV)
     stats = torch.zeros((3,), dtype=torch.int64, device=DEV)
+    segb = _lib.query("gs_render_seg_bytes", R, T) if seg else 0
+    # NaN-filled: the backward must only read checkpoints the forward wrote
+    seg_ws = torch.full((segb // 4,), float("nan"), device=DEV).view(torch.uint8) if seg else None
     _lib.call("gs_render_forward", P, R, H, W, means2D.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(),
               offsets.data_ptr(), rec.data_ptr(), bg_t.data_ptr(), tiles[0].data_ptr(), ids[0].data_ptr(),
               tiles[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(), image.data_ptr(),
-              final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), stream())
+              final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), _lib.ptr(seg_ws), segb, stream())
     torch.cuda.synchronize()
     # the 64-bit keys of the published algorithm, rebuilt from the sorted (tile, splat id) pairs
     ids_s, tiles_s = ids[1][:R].to(torch.int64) & 0xffffffff, tiles[1][:R].to(torch.int64) & 0xffffffff
     dbits = depths.view(torch.int32).to(torch.int64) & 0xffffffff
     keys = (tiles_s << 32) | dbits[ids_s] if R > 0 else torch.zeros((0,), dtype=torch.int64, device=DEV)
     return dict(R=R, offsets=offsets, order=order, rec=rec, keys=keys, ids=ids[1][:R], ids_buf=ids[1], ranges=ranges,
-                image=image, final_T=final_T, n_contrib=n_contrib, stats=stats, cl=cl, bg=bg_t, P=P, H=H, W=W)
+                image=image, final_T=final_T, n_contrib=n_contrib, stats=stats, cl=cl, bg=bg_t, P=P, H=H, W=W,
+                seg_ws=seg_ws, seg_bytes=segb)
 
 
 def render_backward(f, dL_dimage):
@@ -103,7 +108,7 @@ def render_backward(f, dL_dimage):
                rgb=torch.full((P, 3), float("nan"), device=DEV))
     _lib.call("gs_render_backward", P, f["R"], f["H"], f["W"], f["rec"].data_ptr(), f["bg"].data_ptr(),
               f["cl"].data_ptr(), f["ranges"].data_ptr(), f["ids_buf"].data_ptr(), f["final_T"].data_ptr(),
-              f["n_contrib"].data_ptr(), dL_dimage.data_ptr(), out["means2D"].data_ptr(),
+              f["n_contrib"].data_ptr(), dL_dimage.data_ptr(), _lib.ptr(f["seg_ws"]), f["seg_bytes"], out["means2D"].data_ptr(),
               out["conic_opacity"].data_ptr(), out["rgb"].data_ptr(), stream())
     torch.cuda.synchronize()
     return out

@@ -151,30 +151,36 @@ def test_render_backward_parity(o32, n, W, H, rad, bg):
         assert (a[untouched] == 0).all()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GS_B200_EXPERIMENTAL") != "1",
-                    reason="experimental kernels (off by default): set GS_B200_EXPERIMENTAL=1 to validate them")
-@pytest.mark.parametrize("flag", ["DEBUG_BWD_WHT_64", "DEBUG_BWD_WHT_128", "DEBUG_BWD_AUTO"])
 @pytest.mark.parametrize("n,W,H,rad,bg", [(20000, 320, 200, 7.0, (0.0, 0.0, 0.0)), (3000, 96, 64, 16.0, (0.3, 0.1, 0.7)),
-                                          (30000, 200, 120, 9.0, (0.2, 0.5, 0.9))])
-def test_experimental_backward_wht_parity(o32, flag, n, W, H, rad, bg):
-    """k_blend_bwd_wht (Walsh-Hadamard moment reduction, gs_debug_set) against the oracle and the default kernel."""
+                                          (30000, 200, 120, 9.0, (0.2, 0.5, 0.9)), (60000, 100, 70, 12.0, (0.1, 0.2, 0.3))])
+def test_backward_kernels_agree(o32, n, W, H, rad, bg):
+    """The segment-parallel backward (default: checkpoints written by the forward, one warp per (tile, 64-entry segment))
+    against the oracle AND against the tile-parallel kernel (gs_debug_set(GS_DEBUG_BWD_TILE) / no segment workspace);
+    the forward's image does not depend on whether it writes checkpoints.  The last case has ~900-entry tile lists
+    (many segments per tile)."""
     from gs_b200 import _lib
     ref, rf, f, cl = _render_case(o32, n, W, H, rad, bg)
     g = np.random.default_rng(2).normal(size=(3, H, W)).astype(np.float32)
     rb = o32.render_backward(H, W, ref["means2D"], ref["conic_opacity"], ref["rgb"], bg, rf, g)
-    base = gu.render_backward(f, gu.to_dev(g))
-    old = _lib.debug_set(getattr(_lib, flag))
+    got = gu.render_backward(f, gu.to_dev(g))
+    old = _lib.debug_set(_lib.DEBUG_BWD_TILE)
     try:
-        got = gu.render_backward(f, gu.to_dev(g))
+        tile = gu.render_backward(f, gu.to_dev(g))
     finally:
         _lib.debug_set(old)
+    f2 = gu.render_forward(H, W, gu.to_dev(ref["means2D"]), gu.to_dev(ref["conic_opacity"]), gu.to_dev(ref["rgb"]),
+                           gu.to_dev(ref["depths"]), gu.to_dev(ref["radii"]), gu.to_dev(cl), bg, seg=False)
+    assert torch.equal(f2["image"], f["image"]) and torch.equal(f2["n_contrib"], f["n_contrib"])
+    tile2 = gu.render_backward(f2, gu.to_dev(g))
     for k in ("means2D", "conic_opacity", "rgb"):
         a = gu.npy(got[k])
         assert np.isfinite(a).all()
-        frac, _ = gu.rel_report(f"{flag}.{k}", a, rb[k])
+        frac, _ = gu.rel_report(f"seg.{k}", a, rb[k])
         assert frac <= 5 * OUTLIER_FRAC, k
-        frac2, _ = gu.rel_report(f"{flag}.vs_default.{k}", a, gu.npy(base[k]))
+        frac2, _ = gu.rel_report(f"seg.vs_tile.{k}", a, gu.npy(tile[k]))
         assert frac2 <= 5 * OUTLIER_FRAC, k
+        frac3, _ = gu.rel_report(f"tile.{k}", gu.npy(tile2[k]), rb[k])
+        assert frac3 <= 5 * OUTLIER_FRAC, k
         assert (a[~np.isin(np.arange(n), rf["ids"])] == 0).all()
 
 
