@@ -88,7 +88,9 @@ struct __align__(16) SRec { float4 a; float4 b; float4 c; };
 // SEG_K entries per segment.  Checkpoint slot of (tile t, boundary after segment s) = ranges[t].x / SEG_K + t + s:
 // injective over all tiles without a scan (floor((x+l)/K) - floor(x/K) >= ceil(l/K) - 1), < R / SEG_K + T + 1.
 // A slot holds one float4 per pixel, in the BACKWARD's order: index = (8x4 block) * 32 + lane.
-#define SEG_K 64
+#ifndef SEG_K
+#define SEG_K 128
+#endif
 #define SEG_SLOT 256
 struct SegWs {
     uint32_t *n_units;    // [1] number of (tile, segment) units appended by the forward
@@ -113,8 +115,11 @@ static SegWs seg_carve(void *ws, int64_t R, int64_t T) {
 }
 extern "C" size_t gs_render_seg_bytes(int64_t R, int num_tiles) { return seg_bytes(R > 0 ? R : 0, num_tiles > 0 ? num_tiles : 0); }
 
+#ifndef FW_MIN_CTAS
+#define FW_MIN_CTAS 6
+#endif
 template <bool STATS, bool CKPT>
-__global__ void __launch_bounds__(BL_THREADS)
+__global__ void __launch_bounds__(BL_THREADS, FW_MIN_CTAS)
 k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
             const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
             const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
@@ -254,6 +259,183 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
         __syncthreads();
         unsigned long long v0 = inside ? (unsigned long long)total : 0ull, v1 = inside ? considered : 0u,
                            v2 = inside ? blended : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(FULL, v0, o);
+            v1 += __shfl_xor_sync(FULL, v1, o);
+            v2 += __shfl_xor_sync(FULL, v2, o);
+        }
+        if (lane == 0) { atomicAdd(&s_stats[0], v0); atomicAdd(&s_stats[1], v1); atomicAdd(&s_stats[2], v2); }
+        __syncthreads();
+        if (threadIdx.x < 3) atomicAdd(&stats[3 * view + threadIdx.x], s_stats[threadIdx.x]);
+    }
+}
+
+// ---- forward, packed variant: TWO pixels per lane, four 4x4 blocks per warp --------------------------------------------
+// One CTA of 4 warps per tile.  Warp w owns the 16x4 pixel strip of rows 4w..4w+3, i.e. four 4x4 blocks; each QUARTER
+// warp (8 lanes) owns one block and walks its own candidate list, each lane blending two horizontally adjacent pixels
+// with packed fp32 arithmetic (fma.rn.f32x2 & co: one issue slot for both pixels).  One warp instruction therefore
+// advances four (block, splat) pairs instead of two; the per-pixel arithmetic is the same operation sequence as
+// k_blend_fwd (bit-identical images).
+#define F2_THREADS 128
+#define F2_WARPS 4
+#ifndef F2_MIN_CTAS
+#define F2_MIN_CTAS 8
+#endif
+GS_D float2 f2(float a) { return make_float2(a, a); }
+
+template <bool STATS, bool CKPT>
+__global__ void __launch_bounds__(F2_THREADS, F2_MIN_CTAS)
+k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
+             const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
+             const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
+             uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats, const SegWs seg) {
+    __shared__ SRec s_rec[FW_CHUNK];
+    __shared__ uint16_t s_cull[FW_CHUNK];
+    __shared__ unsigned long long s_stats[3];
+    __shared__ uint32_t s_red[F2_WARPS + 2];
+    const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X;
+    const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quarter = lane >> 3, l8 = lane & 7;
+    const int blk = warp * 4 + quarter;                       // 4x4 block: column = quarter, row = warp
+    const int lx = quarter * 4 + (l8 & 1) * 2, ly = warp * 4 + (l8 >> 1);  // first pixel of the pair, inside the tile
+    const int px = (tile % gx) * GS_BLOCK_X + lx, py = (tile / gx) * GS_BLOCK_Y + ly;
+    const bool in0 = px < W && py < H, in1 = px + 1 < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)py * W + px;
+    image += (size_t)view * 3 * HW;
+    final_T += (size_t)view * HW;
+    n_contrib += (size_t)view * HW;
+    if (!compute_locally[blockIdx.x]) {  // non-local tiles must read exactly 0 (loss_distribution.py:1875)
+        if (in0) { image[pix] = 0.f; image[HW + pix] = 0.f; image[2 * HW + pix] = 0.f; }
+        if (in1) { image[pix + 1] = 0.f; image[HW + pix + 1] = 0.f; image[2 * HW + pix + 1] = 0.f; }
+        if (CKPT && threadIdx.x == 0) seg.tile_last[blockIdx.x] = 0u;
+        return;
+    }
+    const uint2 range = ranges[blockIdx.x];
+    const int total = (int)(range.y - range.x);
+    const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
+    const float qnan = __int_as_float(0x7fc00000);
+    // minus the pixel coordinates; NaN = finished / outside pixel, which then never passes a test
+    float2 npx = make_float2(in0 ? -(float)px : qnan, in1 ? -(float)(px + 1) : qnan);
+    const float pyf = (float)py;
+    float2 T = f2(1.f), C0 = f2(0.f), C1 = f2(0.f), C2 = f2(0.f), Ct0 = f2(0.f), Ct1 = f2(0.f), Ct2 = f2(0.f);
+    uint32_t last0 = 0, last1 = 0, blended = 0, cons0 = 0, cons1 = 0;
+    bool done0 = !in0, done1 = !in1;
+    // this pixel pair's entries in a checkpoint slot: (8x4 block) * 32 + (row in block) * 8 + (column in block)
+    float4 *ck = nullptr;
+    int nck = 0;
+    if (CKPT)
+        ck = seg.ckpt + ((size_t)(range.x / SEG_K) + blockIdx.x) * SEG_SLOT + (warp * 2 + (lx >> 3)) * 32 + (ly & 3) * 8 + (lx & 7);
+    for (int base = 0; base < total; base += FW_CHUNK) {
+        if (__syncthreads_count(done0 && done1) == F2_THREADS) break;
+        const int cnt = min(FW_CHUNK, total - base);
+        for (int i = threadIdx.x; i < cnt; i += F2_THREADS) {
+            const uint32_t g = ids[range.x + base + i];
+            const float4 *r = rec + (size_t)3 * g;
+            const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+            s_rec[i].a = a; s_rec[i].b = b; s_rec[i].c = c;
+            s_cull[i] = (uint16_t)block_mask16(a.x, a.y, c.z, c.w, X0, Y0);
+        }
+        __syncthreads();
+        for (int g0 = 0; g0 < cnt; g0 += 32) {
+            if (__all_sync(FULL, done0 && done1)) break;
+            {   // segment boundary (see k_blend_fwd)
+                const int e0 = base + g0;
+                if (e0 > 0 && (e0 & (SEG_K - 1)) == 0) {
+                    if (CKPT) {
+                        ck[(size_t)nck * SEG_SLOT] = make_float4(T.x, C0.x, C1.x, C2.x);
+                        ck[(size_t)nck * SEG_SLOT + 1] = make_float4(T.y, C0.y, C1.y, C2.y);
+                        nck++;
+                    }
+                    Ct0 = __fadd2_rn(Ct0, C0); Ct1 = __fadd2_rn(Ct1, C1); Ct2 = __fadd2_rn(Ct2, C2);
+                    C0 = C1 = C2 = f2(0.f);
+                }
+            }
+            // lane l inspects entry g0 + 31 - l: the HIGHEST set bit of a ballot is the EARLIEST candidate
+            const int jj = g0 + 31 - lane;
+            const uint32_t m = jj < cnt ? ((uint32_t)s_cull[jj] >> (warp * 4)) : 0u;
+            const uint32_t c0 = __ballot_sync(FULL, m & 1u), c1 = __ballot_sync(FULL, m & 2u),
+                           c2 = __ballot_sync(FULL, m & 4u), c3 = __ballot_sync(FULL, m & 8u);
+            uint32_t mine = quarter == 0 ? c0 : quarter == 1 ? c1 : quarter == 2 ? c2 : c3;
+            while (__any_sync(FULL, mine != 0u)) {
+                const bool has = mine != 0u;
+                const int lz = __clz((int)mine);       // 32 when empty
+                const int j = g0 + (has ? lz : 0);
+                mine &= ~(0x80000000u >> lz);
+                const SRec *sr = &s_rec[j];
+                const float4 a = sr->a, b = sr->b;
+                const float dy = a.y - pyf;
+                const float2 dx = __fadd2_rn(f2(a.x), npx);
+                const float t = a.w * dy, u = b.x * dy * dy;
+                const float2 pw = __ffma2_rn(dx, __ffma2_rn(f2(a.z), dx, f2(t)), f2(u));
+                const bool ok0 = has && pw.x >= b.z, ok1 = has && pw.y >= b.z;  // false for NaN
+                if (!__any_sync(FULL, ok0 || ok1)) continue;
+                const float2 e = __fmul2_rn(pw, f2(1.4426950408889634f));
+                float2 G;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G.x) : "f"(e.x));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G.y) : "f"(e.y));
+                float2 alpha = __fmul2_rn(f2(b.y), G);
+                alpha.x = fminf(ALPHA_MAX, alpha.x); alpha.y = fminf(ALPHA_MAX, alpha.y);
+                const bool v0 = ok0 && pw.x <= 0.f && alpha.x >= ALPHA_MIN, v1 = ok1 && pw.y <= 0.f && alpha.y >= ALPHA_MIN;
+                const float2 test_T = __fmul2_rn(T, __ffma2_rn(alpha, f2(-1.f), f2(1.f)));
+                const bool end0 = v0 && test_T.x < T_EPS, end1 = v1 && test_T.y < T_EPS;
+                const bool bl0 = v0 && !end0, bl1 = v1 && !end1;
+                if (end0) { done0 = true; npx.x = qnan; if (STATS) cons0 = (uint32_t)(base + j + 1); }
+                if (end1) { done1 = true; npx.y = qnan; if (STATS) cons1 = (uint32_t)(base + j + 1); }
+                float2 w = __fmul2_rn(alpha, T);
+                w.x = bl0 ? w.x : 0.f; w.y = bl1 ? w.y : 0.f;
+                const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
+                C0 = __ffma2_rn(f2(b.w), w, C0); C1 = __ffma2_rn(f2(gb.x), w, C1); C2 = __ffma2_rn(f2(gb.y), w, C2);
+                T.x = bl0 ? test_T.x : T.x; T.y = bl1 ? test_T.y : T.y;
+                last0 = bl0 ? (uint32_t)(base + j + 1) : last0; last1 = bl1 ? (uint32_t)(base + j + 1) : last1;
+                if (STATS) blended += (bl0 ? 1u : 0u) + (bl1 ? 1u : 0u);
+            }
+        }
+    }
+    const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+    if (in0) {
+        image[pix] = (Ct0.x + C0.x) + T.x * b0; image[HW + pix] = (Ct1.x + C1.x) + T.x * b1; image[2 * HW + pix] = (Ct2.x + C2.x) + T.x * b2;
+        final_T[pix] = T.x; n_contrib[pix] = last0;
+        if (cons0 == 0) cons0 = (uint32_t)total;
+    }
+    if (in1) {
+        image[pix + 1] = (Ct0.y + C0.y) + T.y * b0; image[HW + pix + 1] = (Ct1.y + C1.y) + T.y * b1; image[2 * HW + pix + 1] = (Ct2.y + C2.y) + T.y * b2;
+        final_T[pix + 1] = T.y; n_contrib[pix + 1] = last1;
+        if (cons1 == 0) cons1 = (uint32_t)total;
+    }
+    if (CKPT) {
+        float2 r0 = C0, r1 = C1, r2 = C2;
+        for (int s = nck - 1; s >= 0; s--) {
+            const float4 ca = ck[(size_t)s * SEG_SLOT], cb = ck[(size_t)s * SEG_SLOT + 1];
+            ck[(size_t)s * SEG_SLOT] = make_float4(ca.x, r0.x, r1.x, r2.x);
+            ck[(size_t)s * SEG_SLOT + 1] = make_float4(cb.x, r0.y, r1.y, r2.y);
+            r0.x += ca.y; r1.x += ca.z; r2.x += ca.w;
+            r0.y += cb.y; r1.y += cb.z; r2.y += cb.w;
+        }
+        uint32_t m = max(in0 ? last0 : 0u, in1 ? last1 : 0u);
+        m = __reduce_max_sync(FULL, m);
+        if (lane == 0) s_red[warp] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tl = 0;
+#pragma unroll
+            for (int w = 0; w < F2_WARPS; w++) tl = max(tl, s_red[w]);
+            const uint32_t nseg = (tl + SEG_K - 1) / SEG_K;
+            seg.tile_last[blockIdx.x] = tl;
+            s_red[F2_WARPS] = nseg;
+            s_red[F2_WARPS + 1] = nseg ? atomicAdd(seg.n_units, nseg) : 0u;
+        }
+        __syncthreads();
+        const uint32_t nseg = s_red[F2_WARPS], ubase = s_red[F2_WARPS + 1];
+        for (uint32_t i = threadIdx.x; i < nseg; i += F2_THREADS) seg.units[ubase + i] = make_uint2(blockIdx.x, nseg - 1 - i);
+    }
+    if (STATS) {  // stages 81-83: sums of tile-list length / entries walked / entries blended
+        if (threadIdx.x < 3) s_stats[threadIdx.x] = 0ull;
+        __syncthreads();
+        unsigned long long v0 = (in0 ? (unsigned long long)total : 0ull) + (in1 ? (unsigned long long)total : 0ull),
+                           v1 = (in0 ? cons0 : 0u) + (unsigned long long)(in1 ? cons1 : 0u), v2 = blended;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             v0 += __shfl_xor_sync(FULL, v0, o);
@@ -479,7 +661,14 @@ k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
 #define SG_THREADS (SG_WARPS * 32)
 #define SG_STAGE 32  // records staged per pass: one per lane
 
-__global__ void __launch_bounds__(SG_THREADS, 6)
+#ifndef SG_MIN_CTAS
+#define SG_MIN_CTAS 6
+#endif
+// values needed only when a pass is staged (every 32 entries) or in the per-splat tail live in shared memory, not in
+// registers: the walk keeps 16 state + 9 sum + 12 record registers per lane and wants 8 CTAs per SM
+struct SegCold { const uint32_t *ids; int cnt, X0, Y0; uint32_t blive, blive_hi; };
+
+__global__ void __launch_bounds__(SG_THREADS, SG_MIN_CTAS)
 k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
                 const uint2 *__restrict__ ranges, const uint32_t *__restrict__ ids, const float *__restrict__ final_T,
                 const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage, const SegWs seg,
@@ -487,6 +676,8 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
     __shared__ SRec s_rec_all[SG_WARPS][SG_STAGE];   // c = (green, blue, 1 / opacity, splat id bits)
     __shared__ float4 s_pix_all[SG_WARPS][8 * 32];   // per pixel: dL/dpixel (3) and the number of live entries (int bits)
     __shared__ uint32_t s_mask_all[SG_WARPS][SG_STAGE];
+    __shared__ uint4 s_role_all[SG_WARPS][32];       // per lane: RED target pointer (lo, hi), row stride, scale bits
+    __shared__ SegCold s_cold_all[SG_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t u = blockIdx.x * SG_WARPS + warp;
     if (u >= *seg.n_units) return;  // warps are independent: no CTA-level synchronisation anywhere below
@@ -535,31 +726,43 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
         const uint32_t m = __reduce_max_sync(FULL, (uint32_t)live);
         if (b < 4) blive |= m << (8 * b); else blive_hi |= m << (8 * (b - 4));
     }
-    // lane roles of the final RED: lanes 0,4,...,28 hold sums 0..7 after the butterfly, lane 1 sends sum 8
-    const int role = (lane & 3) == 0 ? (lane >> 2) : (lane == 1 ? 8 : -1);
-    float *rptr = d_means2D;
-    int rstride = 0;
-    float rscale = 0.f;
-    if (role >= 0) {
-        if (role < 2) { rptr = d_means2D + role; rstride = 2; rscale = role == 0 ? 0.5f * (float)W : 0.5f * (float)H; }
-        else if (role < 6) { rptr = d_conic_opacity + (role - 2); rstride = 4; rscale = role == 3 ? -1.f : (role == 5 ? 1.f : -0.5f); }
-        else { rptr = d_rgb + (role - 6); rstride = 3; rscale = 1.f; }
+    {   // lane roles of the final RED: lanes 0,4,...,28 hold sums 0..7 after the butterfly, lane 1 sends sum 8
+        const int role = (lane & 3) == 0 ? (lane >> 2) : (lane == 1 ? 8 : -1);
+        float *rptr = nullptr;
+        uint32_t rstride = 0;
+        float rscale = 0.f;
+        if (role >= 0) {
+            if (role < 2) { rptr = d_means2D + role; rstride = 2; rscale = role == 0 ? 0.5f * (float)W : 0.5f * (float)H; }
+            else if (role < 6) { rptr = d_conic_opacity + (role - 2); rstride = 4; rscale = role == 3 ? -1.f : (role == 5 ? 1.f : -0.5f); }
+            else { rptr = d_rgb + (role - 6); rstride = 3; rscale = 1.f; }
+        }
+        const unsigned long long rp = (unsigned long long)rptr;
+        s_role_all[warp][lane] = make_uint4((uint32_t)rp, (uint32_t)(rp >> 32), rstride, __float_as_uint(rscale));
+        if (lane == 0) {
+            SegCold c;
+            c.ids = ids + range.x + seg_base; c.cnt = cnt; c.X0 = X0; c.Y0 = Y0; c.blive = blive; c.blive_hi = blive_hi;
+            s_cold_all[warp] = c;
+        }
     }
+    const uint4 *s_role = &s_role_all[warp][lane];
+    const SegCold *s_cold = &s_cold_all[warp];
     const float pxf0 = (float)(X0 + (lane & 7)), pyf0 = (float)(Y0 + (lane >> 3));
     for (int pass = (cnt - 1) / SG_STAGE; pass >= 0; pass--) {
         // stage 32 records, one per lane; entry i keeps only the blocks it can reach (bounding box of {alpha >= 1/255})
         // that still have a live pixel at depth i
-        const int p0 = pass * SG_STAGE, pn = min(SG_STAGE, cnt - p0);
+        const int p0 = pass * SG_STAGE;
         __syncwarp();
+        const SegCold cold = *s_cold;
+        const int pn = min(SG_STAGE, cold.cnt - p0);
         if (lane < pn) {
             const int i = p0 + lane;
-            const uint32_t g = ids[range.x + seg_base + i];
+            const uint32_t g = cold.ids[i];
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-            uint32_t m = block_mask(a.x, a.y, c.z, c.w, (float)X0, (float)Y0);
+            uint32_t m = block_mask(a.x, a.y, c.z, c.w, (float)cold.X0, (float)cold.Y0);
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const uint32_t bl = ((q < 4 ? blive : blive_hi) >> (8 * (q & 3))) & 0xffu;
+                const uint32_t bl = ((q < 4 ? cold.blive : cold.blive_hi) >> (8 * (q & 3))) & 0xffu;
                 if ((uint32_t)i >= bl) m &= ~(1u << q);
             }
             s_rec[lane].a = a; s_rec[lane].b = b;
@@ -573,7 +776,8 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
             const uint32_t m8 = __reduce_or_sync(FULL, s_mask[jl]);
             if (m8 == 0u) continue;
             const int j = p0 + jl;
-            const float4 a = s_rec[jl].a, b4 = s_rec[jl].b, c4 = s_rec[jl].c;
+            const float4 a = s_rec[jl].a, b4 = s_rec[jl].b;
+            const float2 c4 = *reinterpret_cast<const float2 *>(&s_rec[jl].c);  // (green, blue)
             const float mxl = a.x - pxf0, myl = a.y - pyf0;
             float v[9];
 #pragma unroll
@@ -613,11 +817,13 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
                 const float sx = v[0], sy = v[1];
                 v[0] = 2.f * a.z * sx + a.w * sy;
                 v[1] = 2.f * b4.x * sy + a.w * sx;
-                v[5] *= c4.z;
+                v[5] *= s_rec[jl].c.z;
             }
             warp_reduce9(v, lane);
-            const float val = (lane == 1 ? v[8] : v[0]) * rscale;
-            if (role >= 0) atomicAdd(rptr + (size_t)__float_as_uint(c4.w) * rstride, val);
+            const uint4 ro = *s_role;
+            const float val = (lane == 1 ? v[8] : v[0]) * __uint_as_float(ro.w);
+            float *rptr = reinterpret_cast<float *>((unsigned long long)ro.x | ((unsigned long long)ro.y << 32));
+            if (rptr) atomicAdd(rptr + (size_t)__float_as_uint(s_rec[jl].c.w) * ro.z, val);
         }
     }
 }
@@ -626,9 +832,14 @@ template <bool STATS, bool CKPT>
 static void launch_fwd(int grid, cudaStream_t stream, int W, int H, int T1, const float *rec, const float *bg,
                        const uint8_t *cl, const uint32_t *ranges, const uint32_t *ids, float *image, float *final_T,
                        uint32_t *n_contrib, int64_t *stats, const SegWs &seg) {
-    k_blend_fwd<STATS, CKPT><<<grid, BL_THREADS, 0, stream>>>(
-        W, H, T1, reinterpret_cast<const float4 *>(rec), bg, cl, reinterpret_cast<const uint2 *>(ranges), ids, image,
-        final_T, n_contrib, reinterpret_cast<unsigned long long *>(stats), seg);
+    if (g_gs_debug_flags & GS_DEBUG_FWD_HALFWARP)
+        k_blend_fwd<STATS, CKPT><<<grid, BL_THREADS, 0, stream>>>(
+            W, H, T1, reinterpret_cast<const float4 *>(rec), bg, cl, reinterpret_cast<const uint2 *>(ranges), ids, image,
+            final_T, n_contrib, reinterpret_cast<unsigned long long *>(stats), seg);
+    else
+        k_blend_fwd2<STATS, CKPT><<<grid, F2_THREADS, 0, stream>>>(
+            W, H, T1, reinterpret_cast<const float4 *>(rec), bg, cl, reinterpret_cast<const uint2 *>(ranges), ids, image,
+            final_T, n_contrib, reinterpret_cast<unsigned long long *>(stats), seg);
 }
 
 int gs_launch_blend_forward(int num_views, int64_t R, int H, int W, const float *rec, const float *bg,

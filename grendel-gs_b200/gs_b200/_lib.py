@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libgrendel_gs_b200.so")
+# GS_B200_LIB: a tuning build of the same library (gs_b200.build.build(variant=...)); default = the shipped one
+LIB_PATH = os.environ.get("GS_B200_LIB") or os.path.join(_PKG, "lib", "libgrendel_gs_b200.so")
 
 _vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 
@@ -129,6 +130,7 @@ def ptr(t):
 STAGE_NUM = 14
 DEBUG_NO_BLOCK_CULL = 1
 DEBUG_BWD_TILE = 2       # gs_render_backward: round 1's tile-parallel kernel instead of the segment-parallel one
+DEBUG_FWD_HALFWARP = 4   # gs_render_forward: round 1's half-warp blend kernel instead of the packed two-pixel one
 
 
 def debug_set(flags):

@@ -43,18 +43,25 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu for sm_100a and link the shared library. Returns the library path."""
+def build(force=False, verbose=False, defs=(), variant=None):
+    """Compile every .cu for sm_100a and link the shared library. Returns the library path.
+    defs / variant: tuning builds -- extra -D flags, linked as lib/libgrendel_gs_b200.<variant>.so (selected at run time
+    with GS_B200_LIB=<path>; A/B of compile-time parameters in one device call)."""
+    lib_out, objdir = LIB, OBJDIR
+    if variant:
+        lib_out = os.path.join(LIBDIR, f"libgrendel_gs_b200.{variant}.so")
+        objdir = os.path.join(PKG, "build", variant)
+        force = True
     if not force and not is_stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     cc = nvcc()
     logs = {}
 
     def compile_one(src):
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [cc, *ARCH, *COMMON, *PER_FILE.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [cc, *ARCH, *COMMON, *PER_FILE.get(src, []), *defs, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs[src] = r.stderr
         if r.returncode != 0:
@@ -63,17 +70,17 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [cc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+    cmd = [cc, *ARCH, "-shared", "-o", lib_out, *objs, "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(os.path.join(OBJDIR, "ptxas.log"), "w") as f:
+    with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         for k in sorted(logs):
             f.write(f"==== {k}\n{logs[k]}\n")
     if verbose:
         for k in sorted(logs):
             print(f"==== {k}\n{logs[k]}")
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":

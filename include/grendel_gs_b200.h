@@ -255,7 +255,10 @@ enum {
     GS_DEBUG_NO_BLOCK_CULL = 1,
     /* gs_render_backward: use the tile-parallel kernel of round 1 (one CTA per tile, k_blend_bwd) even when a segment
      * workspace is passed -- A/B timing and cross-checking of the two backward kernels. */
-    GS_DEBUG_BWD_TILE = 2
+    GS_DEBUG_BWD_TILE = 2,
+    /* gs_render_forward: the half-warp-per-4x4-block blend kernel of round 1 (k_blend_fwd) instead of the packed
+     * two-pixels-per-lane kernel (k_blend_fwd2); the images are bit-identical. */
+    GS_DEBUG_FWD_HALFWARP = 4
 };
 GS_API int gs_debug_set(int flags);
 

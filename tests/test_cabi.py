@@ -93,8 +93,14 @@ def test_argument_errors_are_reported_not_crashed(lib):
 
 def test_dropin_package_exports_reference_names():
     import diff_gaussian_rasterization as d
-    import gsplat
     from simple_knn._C import distCUDA2  # noqa: F401
+    # the gsplat stub is opt-in (shims/): it must not shadow a real gsplat install on the package path
+    import importlib.util
+    assert not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(d.__file__)), "gsplat"))
+    spec = importlib.util.spec_from_file_location("gsplat_stub", os.path.join(os.path.dirname(os.path.dirname(d.__file__)),
+                                                                              "shims", "gsplat", "__init__.py"))
+    gsplat = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gsplat)
     assert d._C.get_block_XY() == (16, 16, 256)
     for n in ("GaussianRasterizationSettings", "GaussianRasterizer"):
         assert hasattr(d, n)
