@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", help="c2 = 2M Gaussians @1920x1080 (BASELINE.json configs[1])")
     ap.add_argument("--n", type=int, default=0, help="override Gaussian count")
+    ap.add_argument("--views", type=int, default=0, help="cameras per step (bsz); default = --gpus (one view per GPU, weak "
+                    "scaling); fewer views than GPUs shards every render into tile-row strips over several GPUs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the untimed extras at N > 1 (strong-scaling leg, parity)")
     ap.add_argument("--cpu-sample", type=int, default=250_000, help="Gaussians in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--time-optimizer", action="store_true",
@@ -146,15 +149,21 @@ def cpu_arm(cfg, sample_n, steps, warmup):
     cam = syn.make_camera(W, H)
     sc = syn.make_scene(n, W, H, seed=0)
     gt = syn.make_gt_image(W, H)
+    steps, warmup = max(3, steps), max(2, warmup)
     for _ in range(warmup):
-        o.train_step(sc, cam, gt)
-    t0 = time.perf_counter()
+        out = o.train_step(sc, cam, gt)
+    ts = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         o.train_step(sc, cam, gt)
-    dt = (time.perf_counter() - t0) / steps
-    return dict(value=n / dt, unit=UNIT, cores=cores, kind="port", ms_per_step=dt * 1e3,
-                sample=f"{n} of {cfg['n']} Gaussians (seed 0, same distribution) on the full {W}x{H} view, "
-                       f"forward+loss+backward, oracle/gs_oracle.c with OpenMP on {cores} threads")
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.median(ts))
+    V, R = int((out["pre"]["radii"] > 0).sum()), int(out["fwd"]["R"])
+    return dict(value=n / dt, unit=UNIT, cores=cores, kind="port", ms_per_step=dt * 1e3, steps=steps, warmup=warmup,
+                ms_min=min(ts) * 1e3, ms_max=max(ts) * 1e3, visible=V, instances_R=R,
+                sample=f"{n} of {cfg['n']} Gaussians (seed 0, same distribution; realised V = {V}, R = {R}) on the full "
+                       f"{W}x{H} view, forward+loss+backward, oracle/gs_oracle.c with OpenMP on {cores} threads, "
+                       f"median of {steps} steps after {warmup} warm-ups")
 
 
 def run_reference(args):
@@ -165,13 +174,14 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = workload(args)
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    steps, warmup = max(3, min(args.steps, 5)), max(2, min(args.warmup, 2))
     r = cpu_arm(cfg, args.cpu_sample, steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg['n']} Gaussians @ {cfg['width']}x{cfg['height']}, bounded CPU sample"},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_min", "ms_max", "visible",
+                                               "instances_R")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -185,10 +195,43 @@ def alg_bytes(N, V, Vp, R, P, T):
             "loss": 27 * P, "b10 render": 76 * R + 20 * P, "b20 preprocess": 304 * V + 236 * N}
 
 
+def build_trainer(args, cfg, B, dev, rank, world, **kw):
+    """Trainer over B cameras of the workload.  Scenes that fit comfortably on the host (c1, c2) are generated whole on
+    every rank and sliced (the round-1 scene, bit for bit); larger ones (c3, c4) shard-wise, each rank only its own
+    Gaussians (synthetic.make_scene_shard)."""
+    import torch
+    from gs_b200 import pipeline, synthetic as syn
+    W, H, N = cfg["width"], cfg["height"], cfg["n"]
+    cams = syn.make_batch_cameras(W, H, B)
+    gts = [torch.from_numpy(syn.make_gt_image(W, H, seed=1 + k)).pin_memory() for k in range(B)]
+    if N <= 4_000_000:
+        scene = syn.make_scene(N, W, H, seed=0)
+        return pipeline.Trainer(scene, cams, gts, dev, rank, world, **kw)
+    lo, hi = N * rank // world, N * (rank + 1) // world
+    scene = syn.make_scene_shard(N, lo, hi, W, H, seed=0)
+    return pipeline.Trainer(scene, cams, gts, dev, rank, world, shard=(lo, hi, N), **kw)
+
+
+def timed_steps(trainer, steps, resident, barrier_sync):
+    """EXACTLY `steps` steps between a barrier + synchronise on both sides; one CUDA event per step boundary.
+    -> (total ms on this rank, per-step ms list, last return value of step())."""
+    import torch
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    barrier_sync()
+    evs[0].record()
+    out = None
+    for i in range(steps):
+        out = trainer.step(resident=resident)
+        evs[i + 1].record()
+    barrier_sync()
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return evs[0].elapsed_time(evs[steps]), per, out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from gs_b200 import _lib, pipeline, synthetic as syn
+    from gs_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,7 +245,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
-    # A/B of experimental kernels (include/grendel_gs_b200.h, gs_debug_set): GS_B200_DEBUG_FLAGS=2 python bench.py;
+    # A/B of kernel variants (include/grendel_gs_b200.h, gs_debug_set): GS_B200_DEBUG_FLAGS=2 python bench.py;
     # a run with flags set is labelled in config.debug_flags and is NOT the shipped configuration
     debug_flags = int(os.environ.get("GS_B200_DEBUG_FLAGS", "0"))
     if debug_flags:
@@ -210,20 +253,23 @@ def run_ours(args):
 
     cfg = workload(args)
     W, H, N = cfg["width"], cfg["height"], cfg["n"]
-    B = world  # one view per GPU per step: weak scaling in views, Gaussians sharded (README.md:344 "4 GPU bsz 4")
+    # default: one view per GPU per step -- weak scaling in views, Gaussians sharded (README.md:344 "4 GPU bsz 4");
+    # --views B < GPUs shards every render into tile-row strips over several GPUs (the strong-scaling direction)
+    B = args.views or world
     P_pix, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
     steps, warmup = args.steps, max(3, args.warmup)
-
-    scene = syn.make_scene(N, W, H, seed=0)
-    cams = syn.make_batch_cameras(W, H, B)
-    gts = [torch.from_numpy(syn.make_gt_image(W, H, seed=1 + k)).pin_memory() for k in range(B)]
-    trainer = pipeline.Trainer(scene, cams, gts, dev, rank, world)
-    del scene
+    trainer = build_trainer(args, cfg, B, dev, rank, world)
 
     def barrier_sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- leg 1: inputs resident in HBM --------------------------------------------------------
     for _ in range(warmup):
@@ -233,36 +279,22 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     _lib.profile_enable(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier_sync()
-    e0.record()
-    for _ in range(steps):
-        trainer.step(resident=True)
-    e1.record()
-    barrier_sync()
-    ms = e0.elapsed_time(e1)
+    ms, per_step, _ = timed_steps(trainer, steps, True, barrier_sync)
     stages = _lib.profile_read()
     _lib.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / steps
+    ms_step = max_over_ranks(ms) / steps
     info = trainer.last_info()  # realised V, V', R on this rank
+    tot = torch.tensor([info["V"], info["Vp"], info["R"], info["P_local"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)   # the step of ALL ranks: sums over the job
+    job = dict(V=int(tot[0]), Vp=int(tot[1]), R=int(tot[2]), P=int(tot[3]))
 
     # ---- leg 2: end to end through the public operator with HOST buffers ------------------------
     for _ in range(2):
         trainer.step(resident=False)
-    barrier_sync()
-    e0.record()
-    for _ in range(steps):
-        loss_host = trainer.step(resident=False)
-    e1.record()
-    barrier_sync()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item()) / steps
+    ms2, per_step_e2e, loss_host = timed_steps(trainer, steps, False, barrier_sync)
+    ms_e2e = max_over_ranks(ms2) / steps
     h2d, d2h = trainer.io_bytes_per_step()
 
     # ---- optional: the fused Adam step on this rank's six parameter tensors, after both timed regions ------------
@@ -304,6 +336,43 @@ def run_ours(args):
         tt = torch.tensor([trainer.trace[k] / n_tr for k in keys], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         phase_ms = {k: round(float(v), 4) for k, v in zip(keys, tt.tolist())}
+    exchange_kind = None
+    if world > 1:
+        exchange_kind = ("NVLink peer-memory stores fused into the pack kernels (gs_xchg_pack_p2p)"
+                         if trainer._peer is not None else "NCCL all_to_all_single")
+    balance_log = list(trainer.balance_log)
+
+    # ---- extras at N > 1, OUTSIDE the timed regions: (a) the strong-scaling direction the headline does not exercise
+    # (ONE view cut into N strips; N/2 views over N GPUs), (b) multi-GPU parity on a small scene against the CPU oracle
+    extra, parity = None, None
+    if world > 1 and not args.no_extra:
+        extra = {}
+        del trainer
+        torch.cuda.empty_cache()
+        for name, nb in (("strong_1view", 1), (f"views_{world // 2}", world // 2)):
+            if nb < 1 or nb == B or (nb > 1 and name == "strong_1view"):
+                continue
+            tr2 = build_trainer(args, cfg, nb, dev, rank, world)
+            for _ in range(warmup):
+                tr2.step(resident=True)
+            m2, _, _ = timed_steps(tr2, max(5, steps // 2), True, barrier_sync)
+            ms2v = max_over_ranks(m2) / max(5, steps // 2)
+            i2 = tr2.last_info()
+            t2 = torch.tensor([i2["R"], i2["Vp"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t2)
+            extra[name] = {"views_per_step": nb, "ms_per_step": ms2v, "gaussians_per_s": N * nb / (ms2v * 1e-3),
+                           "instances_R_job": int(t2[0]), "splats_rendered_job": int(t2[1]),
+                           "strips_per_view": [len(st.gpu_ids) for st in tr2._strategies],
+                           "division_rows_view0": list(tr2._strategies[0].division_pos),
+                           "division_moves": len(tr2.balance_log) - 1}
+            del tr2
+            torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import mgpu_parity
+            parity = mgpu_parity.check(dev, rank, world, verbose=False)
+        except Exception as e:   # noqa: BLE001 -- a parity failure must show up in the line, not kill the numbers
+            parity = {"ok": False, "error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -318,13 +387,16 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    ab = alg_bytes(N // world * B, info["V"], info["Vp"], info["R"], info["P_local"], T * B)
+    # algorithmic bytes of the step of ALL ranks (every rank preprocesses its shard for all B views, renders the splats it
+    # received, scores its strips) and of rank 0 alone (its kernels are the ones timed by the stage timers below)
+    ab_job = alg_bytes(N * B, job["V"], job["Vp"], job["R"], job["P"], T * B)
+    ab = alg_bytes(trainer_n_local(N, rank, world) * B, info["V"], info["Vp"], info["R"], info["P_local"], T * B)
     per_stage = {k: v[0] / v[1] for k, v in stages.items()}
     launches = {k: v[1] for k, v in stages.items()}
     key_of = {"10 preprocess": "10 preprocess", "70 render": "70 render", "b10 render": "b10 render",
               "b20 preprocess": "b20 preprocess"}
     dom = max(per_stage, key=per_stage.get)
-    units = max(1, launches[dom] // steps)  # launches of that stage per step (one per camera)
+    units = max(1, launches[dom] // steps)  # launches of that stage per step
     if dom in key_of:
         dom_bytes = ab[key_of[dom]] / units
     elif dom.startswith("loss"):
@@ -336,30 +408,36 @@ def run_ours(args):
     # (profiles/traffic.json; only valid for the workload it was captured on: c2 at N=1)
     traffic, secondary = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["stages"]
-        if dom in tj and args.workload == "c2" and world == 1 and not args.n:
-            traffic = tj[dom]["dram_bytes_per_launch"]
-            secondary = {"bound": "instruction issue", "issue_slots_busy_pct": tj[dom]["issue_active_pct"],
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if dom in tj["stages"] and args.workload == "c2" and world == 1 and not args.n and not debug_flags:
+            traffic = tj["stages"][dom]["dram_bytes_per_launch"]
+            secondary = {"bound": "instruction issue", "issue_slots_busy_pct": tj["stages"][dom]["issue_active_pct"],
                          "note": "blend kernels do 256 (pixel,splat) evaluations per 40-76 B instance: issue-bound, "
-                                 "HBM idle by construction (SURVEY.md 8d)", "source": "profiles/r1_all_kernels_ncu.md"}
+                                 "HBM idle by construction (SURVEY.md 8d)", "source": tj.get("source", "profiles/")}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "secondary_bound": secondary, "peak_source": peak_src,
                 "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": per_stage[dom],
                 "stage_ms_per_launch": {k: round(v, 4) for k, v in per_stage.items()},
-                "step_alg_bytes": float(sum(ab.values())),
-                "step_frac_of_hbm_roofline": float(sum(ab.values())) / (ms_step * 1e-3) / 1e9 / peak}
+                "scope": "kernel figures: rank 0's launches; step figures: the whole job (all ranks, all views)",
+                "step_alg_bytes": float(sum(ab_job.values())),
+                "step_frac_of_hbm_roofline": float(sum(ab_job.values())) / (ms_step * 1e-3) / 1e9 / (peak * world)}
 
     value = N * B / (ms_step * 1e-3)
+    spread = lambda v: {"min": round(min(v), 4), "median": round(float(np.median(v)), 4), "max": round(max(v), 4)}
+    scaling = "weak" if B == world or world == 1 else "strong"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {N} Gaussians (sh_degree 3) @ {W}x{H}, {B} view(s)/step, "
                                    f"Gaussians sharded {world} way(s), pixels sharded by tile rows",
-                       "views_per_step": B, "views_per_s": B / (ms_step * 1e-3), "visible": info["V"],
-                       "instances_R": info["R"], "l2_policy": "inputs (472 MB parameters + 0.4 GB binning state) exceed the 126 MB L2",
-                       "loss_check": loss_host},
+                       "views_per_step": B, "views_per_s": B / (ms_step * 1e-3), "visible": job["V"],
+                       "instances_R": job["R"], "splats_rendered": job["Vp"], "counts_scope": "summed over all ranks and views",
+                       "l2_policy": f"inputs ({236 * N // world // 1_000_000} MB parameters per rank + binning state) exceed the 126 MB L2",
+                       "loss_check": loss_host,
+                       "ms_per_step_rank0": {"resident": spread(per_step), "e2e": spread(per_step_e2e),
+                                             "note": "per-step CUDA-event times on rank 0 inside the timed regions"}},
             "e2e": {"value": N * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(sum(v for k, v in launches.items() if k not in ("30 InclusiveSum", "50 SortPairs"))),
@@ -373,14 +451,26 @@ def run_ours(args):
         line["optimizer"] = optimizer
     if phase_ms is not None:  # multi-GPU only; measured outside the timed regions (see above)
         line["phase_ms_serialised"] = phase_ms
-        line["config"]["exchange"] = ("NVLink peer-memory stores fused into the pack kernels (gs_xchg_pack_p2p)"
-                                      if trainer._peer is not None else "NCCL all_to_all_single")
+        line["config"]["exchange"] = exchange_kind
+    if len(balance_log) > 1:
+        line["config"]["load_balance"] = {"division_moves": len(balance_log) - 1, "first": balance_log[0][1][0],
+                                          "last": balance_log[-1][1][0], "note": "tile-row boundaries of view 0 before / after "
+                                          "the timing feedback (finish_strategy_final)"}
+    if extra:
+        line["extra"] = extra
+    if parity is not None:
+        line["config"]["parity"] = parity
     if not args.no_cpu_baseline:
-        r = cpu_arm(cfg, args.cpu_sample, 1, 1)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        r = cpu_arm(cfg, args.cpu_sample, 3, 2)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_min", "ms_max", "visible",
+                                                  "instances_R")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def trainer_n_local(N, rank, world):
+    return N * (rank + 1) // world - N * rank // world
 
 
 def main():

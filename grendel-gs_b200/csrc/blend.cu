@@ -282,7 +282,17 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
 #ifndef F2_MIN_CTAS
 #define F2_MIN_CTAS 8
 #endif
-GS_D float2 f2(float a) { return make_float2(a, a); }
+// Two fp32 values in one 64-bit register, operated on by the packed instructions of sm_100 (FFMA2 / FMUL2 / FADD2).  Kept
+// as opaque 64-bit values so that loop-carried state STAYS packed (float2 variables get scalarised and re-packed with
+// register moves around every packed instruction).
+typedef unsigned long long p2;
+GS_D p2 p2_make(float lo, float hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+GS_D p2 p2_bc(float v) { return p2_make(v, v); }
+GS_D float p2_lo(p2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+GS_D float p2_hi(p2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+GS_D p2 p2_fma(p2 a, p2 b, p2 c) { p2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+GS_D p2 p2_mul(p2 a, p2 b) { p2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+GS_D p2 p2_add(p2 a, p2 b) { p2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 template <bool STATS, bool CKPT>
 __global__ void __launch_bounds__(F2_THREADS, F2_MIN_CTAS)
@@ -298,7 +308,6 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
     const int view = blockIdx.x / tiles_per_view, tile = blockIdx.x - view * tiles_per_view;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int quarter = lane >> 3, l8 = lane & 7;
-    const int blk = warp * 4 + quarter;                       // 4x4 block: column = quarter, row = warp
     const int lx = quarter * 4 + (l8 & 1) * 2, ly = warp * 4 + (l8 >> 1);  // first pixel of the pair, inside the tile
     const int px = (tile % gx) * GS_BLOCK_X + lx, py = (tile / gx) * GS_BLOCK_Y + ly;
     const bool in0 = px < W && py < H, in1 = px + 1 < W && py < H;
@@ -318,9 +327,10 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
     const float X0 = (float)((tile % gx) * GS_BLOCK_X), Y0 = (float)((tile / gx) * GS_BLOCK_Y);
     const float qnan = __int_as_float(0x7fc00000);
     // minus the pixel coordinates; NaN = finished / outside pixel, which then never passes a test
-    float2 npx = make_float2(in0 ? -(float)px : qnan, in1 ? -(float)(px + 1) : qnan);
+    float npx0 = in0 ? -(float)px : qnan, npx1 = in1 ? -(float)(px + 1) : qnan;
     const float pyf = (float)py;
-    float2 T = f2(1.f), C0 = f2(0.f), C1 = f2(0.f), C2 = f2(0.f), Ct0 = f2(0.f), Ct1 = f2(0.f), Ct2 = f2(0.f);
+    const p2 zero2 = p2_bc(0.f), one2 = p2_bc(1.f), mone2 = p2_bc(-1.f);
+    p2 T = one2, C0 = zero2, C1 = zero2, C2 = zero2, Ct0 = zero2, Ct1 = zero2, Ct2 = zero2;
     uint32_t last0 = 0, last1 = 0, blended = 0, cons0 = 0, cons1 = 0;
     bool done0 = !in0, done1 = !in1;
     // this pixel pair's entries in a checkpoint slot: (8x4 block) * 32 + (row in block) * 8 + (column in block)
@@ -345,12 +355,12 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
                 const int e0 = base + g0;
                 if (e0 > 0 && (e0 & (SEG_K - 1)) == 0) {
                     if (CKPT) {
-                        ck[(size_t)nck * SEG_SLOT] = make_float4(T.x, C0.x, C1.x, C2.x);
-                        ck[(size_t)nck * SEG_SLOT + 1] = make_float4(T.y, C0.y, C1.y, C2.y);
+                        ck[(size_t)nck * SEG_SLOT] = make_float4(p2_lo(T), p2_lo(C0), p2_lo(C1), p2_lo(C2));
+                        ck[(size_t)nck * SEG_SLOT + 1] = make_float4(p2_hi(T), p2_hi(C0), p2_hi(C1), p2_hi(C2));
                         nck++;
                     }
-                    Ct0 = __fadd2_rn(Ct0, C0); Ct1 = __fadd2_rn(Ct1, C1); Ct2 = __fadd2_rn(Ct2, C2);
-                    C0 = C1 = C2 = f2(0.f);
+                    Ct0 = p2_add(Ct0, C0); Ct1 = p2_add(Ct1, C1); Ct2 = p2_add(Ct2, C2);
+                    C0 = C1 = C2 = zero2;
                 }
             }
             // lane l inspects entry g0 + 31 - l: the HIGHEST set bit of a ballot is the EARLIEST candidate
@@ -359,6 +369,8 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
             const uint32_t c0 = __ballot_sync(FULL, m & 1u), c1 = __ballot_sync(FULL, m & 2u),
                            c2 = __ballot_sync(FULL, m & 4u), c3 = __ballot_sync(FULL, m & 8u);
             uint32_t mine = quarter == 0 ? c0 : quarter == 1 ? c1 : quarter == 2 ? c2 : c3;
+            const p2 npx = p2_make(npx0, npx1);
+            p2 npx_cur = npx;
             while (__any_sync(FULL, mine != 0u)) {
                 const bool has = mine != 0u;
                 const int lz = __clz((int)mine);       // 32 when empty
@@ -367,52 +379,59 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
                 const SRec *sr = &s_rec[j];
                 const float4 a = sr->a, b = sr->b;
                 const float dy = a.y - pyf;
-                const float2 dx = __fadd2_rn(f2(a.x), npx);
+                const p2 dx = p2_add(p2_bc(a.x), npx_cur);
                 const float t = a.w * dy, u = b.x * dy * dy;
-                const float2 pw = __ffma2_rn(dx, __ffma2_rn(f2(a.z), dx, f2(t)), f2(u));
-                const bool ok0 = has && pw.x >= b.z, ok1 = has && pw.y >= b.z;  // false for NaN
+                const p2 pw = p2_fma(dx, p2_fma(p2_bc(a.z), dx, p2_bc(t)), p2_bc(u));
+                const float pw0 = p2_lo(pw), pw1 = p2_hi(pw);
+                const bool ok0 = has && pw0 >= b.z, ok1 = has && pw1 >= b.z;  // false for NaN
                 if (!__any_sync(FULL, ok0 || ok1)) continue;
-                const float2 e = __fmul2_rn(pw, f2(1.4426950408889634f));
-                float2 G;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G.x) : "f"(e.x));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G.y) : "f"(e.y));
-                float2 alpha = __fmul2_rn(f2(b.y), G);
-                alpha.x = fminf(ALPHA_MAX, alpha.x); alpha.y = fminf(ALPHA_MAX, alpha.y);
-                const bool v0 = ok0 && pw.x <= 0.f && alpha.x >= ALPHA_MIN, v1 = ok1 && pw.y <= 0.f && alpha.y >= ALPHA_MIN;
-                const float2 test_T = __fmul2_rn(T, __ffma2_rn(alpha, f2(-1.f), f2(1.f)));
-                const bool end0 = v0 && test_T.x < T_EPS, end1 = v1 && test_T.y < T_EPS;
+                const p2 e = p2_mul(pw, p2_bc(1.4426950408889634f));
+                float G0, G1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G0) : "f"(p2_lo(e)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G1) : "f"(p2_hi(e)));
+                const p2 araw = p2_mul(p2_bc(b.y), p2_make(G0, G1));
+                const float al0 = fminf(ALPHA_MAX, p2_lo(araw)), al1 = fminf(ALPHA_MAX, p2_hi(araw));
+                const bool v0 = ok0 && pw0 <= 0.f && al0 >= ALPHA_MIN, v1 = ok1 && pw1 <= 0.f && al1 >= ALPHA_MIN;
+                const p2 test_T = p2_mul(T, p2_fma(p2_make(al0, al1), mone2, one2));
+                const bool end0 = v0 && p2_lo(test_T) < T_EPS, end1 = v1 && p2_hi(test_T) < T_EPS;
                 const bool bl0 = v0 && !end0, bl1 = v1 && !end1;
-                if (end0) { done0 = true; npx.x = qnan; if (STATS) cons0 = (uint32_t)(base + j + 1); }
-                if (end1) { done1 = true; npx.y = qnan; if (STATS) cons1 = (uint32_t)(base + j + 1); }
-                float2 w = __fmul2_rn(alpha, T);
-                w.x = bl0 ? w.x : 0.f; w.y = bl1 ? w.y : 0.f;
+                if (end0) { done0 = true; npx0 = qnan; if (STATS) cons0 = (uint32_t)(base + j + 1); }
+                if (end1) { done1 = true; npx1 = qnan; if (STATS) cons1 = (uint32_t)(base + j + 1); }
+                npx_cur = p2_make(npx0, npx1);
+                // effective alpha: 0 for a pixel that does not blend this splat -- every update below is then a no-op, so
+                // the packed state needs no per-component selects (T (1 - ae) is the same product as test_T when blending)
+                const p2 ae = p2_make(bl0 ? al0 : 0.f, bl1 ? al1 : 0.f);
+                const p2 w = p2_mul(ae, T);
                 const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
-                C0 = __ffma2_rn(f2(b.w), w, C0); C1 = __ffma2_rn(f2(gb.x), w, C1); C2 = __ffma2_rn(f2(gb.y), w, C2);
-                T.x = bl0 ? test_T.x : T.x; T.y = bl1 ? test_T.y : T.y;
+                C0 = p2_fma(p2_bc(b.w), w, C0); C1 = p2_fma(p2_bc(gb.x), w, C1); C2 = p2_fma(p2_bc(gb.y), w, C2);
+                T = p2_mul(T, p2_fma(ae, mone2, one2));
                 last0 = bl0 ? (uint32_t)(base + j + 1) : last0; last1 = bl1 ? (uint32_t)(base + j + 1) : last1;
                 if (STATS) blended += (bl0 ? 1u : 0u) + (bl1 ? 1u : 0u);
             }
         }
     }
     const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+    const float T0 = p2_lo(T), T1 = p2_hi(T);
     if (in0) {
-        image[pix] = (Ct0.x + C0.x) + T.x * b0; image[HW + pix] = (Ct1.x + C1.x) + T.x * b1; image[2 * HW + pix] = (Ct2.x + C2.x) + T.x * b2;
-        final_T[pix] = T.x; n_contrib[pix] = last0;
+        image[pix] = (p2_lo(Ct0) + p2_lo(C0)) + T0 * b0; image[HW + pix] = (p2_lo(Ct1) + p2_lo(C1)) + T0 * b1;
+        image[2 * HW + pix] = (p2_lo(Ct2) + p2_lo(C2)) + T0 * b2;
+        final_T[pix] = T0; n_contrib[pix] = last0;
         if (cons0 == 0) cons0 = (uint32_t)total;
     }
     if (in1) {
-        image[pix + 1] = (Ct0.y + C0.y) + T.y * b0; image[HW + pix + 1] = (Ct1.y + C1.y) + T.y * b1; image[2 * HW + pix + 1] = (Ct2.y + C2.y) + T.y * b2;
-        final_T[pix + 1] = T.y; n_contrib[pix + 1] = last1;
+        image[pix + 1] = (p2_hi(Ct0) + p2_hi(C0)) + T1 * b0; image[HW + pix + 1] = (p2_hi(Ct1) + p2_hi(C1)) + T1 * b1;
+        image[2 * HW + pix + 1] = (p2_hi(Ct2) + p2_hi(C2)) + T1 * b2;
+        final_T[pix + 1] = T1; n_contrib[pix + 1] = last1;
         if (cons1 == 0) cons1 = (uint32_t)total;
     }
     if (CKPT) {
-        float2 r0 = C0, r1 = C1, r2 = C2;
+        float r0x = p2_lo(C0), r1x = p2_lo(C1), r2x = p2_lo(C2), r0y = p2_hi(C0), r1y = p2_hi(C1), r2y = p2_hi(C2);
         for (int s = nck - 1; s >= 0; s--) {
             const float4 ca = ck[(size_t)s * SEG_SLOT], cb = ck[(size_t)s * SEG_SLOT + 1];
-            ck[(size_t)s * SEG_SLOT] = make_float4(ca.x, r0.x, r1.x, r2.x);
-            ck[(size_t)s * SEG_SLOT + 1] = make_float4(cb.x, r0.y, r1.y, r2.y);
-            r0.x += ca.y; r1.x += ca.z; r2.x += ca.w;
-            r0.y += cb.y; r1.y += cb.z; r2.y += cb.w;
+            ck[(size_t)s * SEG_SLOT] = make_float4(ca.x, r0x, r1x, r2x);
+            ck[(size_t)s * SEG_SLOT + 1] = make_float4(cb.x, r0y, r1y, r2y);
+            r0x += ca.y; r1x += ca.z; r2x += ca.w;
+            r0y += cb.y; r1y += cb.z; r2y += cb.w;
         }
         uint32_t m = max(in0 ? last0 : 0u, in1 ? last1 : 0u);
         m = __reduce_max_sync(FULL, m);
@@ -662,7 +681,7 @@ k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
 #define SG_STAGE 32  // records staged per pass: one per lane
 
 #ifndef SG_MIN_CTAS
-#define SG_MIN_CTAS 6
+#define SG_MIN_CTAS 8
 #endif
 // values needed only when a pass is staged (every 32 entries) or in the per-splat tail live in shared memory, not in
 // registers: the walk keeps 16 state + 9 sum + 12 record registers per lane and wants 8 CTAs per SM

@@ -15,7 +15,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .division import DivisionStrategy, StrategyHistory, start_strategy  # noqa: F401
+from .division import (DivisionStrategy, StrategyHistory, finish_strategy, heuristics_update_enabled,  # noqa: F401
+                       start_strategy)
 
 
 class RasterSettings:
@@ -114,7 +115,11 @@ class Trainer:
 
     def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None,
                  fused_activations=True, border_exchange=False, batched_render=True, peer_exchange=None,
-                 peer_cap_rows=None):
+                 peer_cap_rows=None, shard=None, load_balance=True, heuristic_decay=0.0):
+        """scene: the WHOLE scene (sliced here into this rank's contiguous shard), or -- shard=(lo, hi, n_total) -- only
+        this rank's Gaussians [lo, hi) of an n_total-Gaussian scene (synthetic.make_scene_shard).
+        load_balance: feed the measured render times back into the strip division after every step
+        (finish_strategy_final, workload_division.py:944-998; only where the reference's gate enables it)."""
         from . import exchange as _ex
         self._ex = _ex
         # splat / gradient rows travel by direct NVLink stores from the pack kernels (exchange.PeerBuffers) instead of
@@ -124,8 +129,11 @@ class Trainer:
             import os as _os
             peer_exchange = _os.environ.get("GS_B200_EXCHANGE", "p2p") != "nccl"
         self._peer = None
+        n = scene["means3D"].shape[0] if shard is None else int(shard[2])
         if world > 1 and peer_exchange:
-            cap = int(peer_cap_rows) if peer_cap_rows else int(1.25 * scene["means3D"].shape[0]) + 65536
+            # every splat of every local camera can land on one rank (bsz views of the scene): rows of the largest
+            # receive / send total.  1.25 x the scene per view, capped by what a step can produce.
+            cap = int(peer_cap_rows) if peer_cap_rows else int(1.25 * n) + 65536
             self._peer = _ex.open_peer_buffers(world, rank, cap, device, group)
         # bin + blend + loss of all B cameras in one pass (ops.render_gaussians_batched) instead of the reference's
         # per-camera loop (render_final, gaussian_renderer/__init__.py:1217-1288); False keeps the per-camera calls
@@ -134,10 +142,18 @@ class Trainer:
         self.lambda_dssim = lambda_dssim
         self.fused_activations = fused_activations
         self.border_exchange = border_exchange   # legacy row L1: exchange 5 halo rows so strip losses sum to the full-image loss
-        n = scene["means3D"].shape[0]
-        lo, hi = n * rank // world, n * (rank + 1) // world
-        self.params = GaussianParams({k: v[lo:hi] for k, v in scene.items()}, device)
+        if shard is None:
+            lo, hi = n * rank // world, n * (rank + 1) // world
+            self.params = GaussianParams({k: v[lo:hi] for k, v in scene.items()}, device)
+        else:
+            lo, hi = int(shard[0]), int(shard[1])
+            if scene["means3D"].shape[0] != hi - lo:
+                raise ValueError("shard=(lo, hi, n_total) does not match the scene passed")
+            self.params = GaussianParams(scene, device)
         self.n_local, self.n_total = hi - lo, n
+        self.load_balance, self.heuristic_decay = load_balance, heuristic_decay
+        self.iteration = 0
+        self.balance_log = []      # (iteration, division rows of camera 0) whenever the division moved
         self.dcams = [DeviceCamera(c, device) for c in cams]
         self.H, self.W = self.dcams[0].image_height, self.dcams[0].image_width
         self.tile_y, self.tile_x = (self.H + 15) // 16, (self.W + 15) // 16
@@ -198,7 +214,14 @@ class Trainer:
         uids = [c.uid for c in self.dcams]
         ver = len(self.history.history)   # the division only changes when the cost heuristic is updated
         if self._strategy_cache is None or self._strategy_cache[0] != ver:
-            self._strategy_cache = (ver, start_strategy(uids, self.history, self.world, self.rank)[0])
+            new = start_strategy(uids, self.history, self.world, self.rank)[0]
+            moved = self._strategy_cache is None or any(
+                a.gpu_ids != b.gpu_ids or a.division_pos != b.division_pos for a, b in zip(new, self._strategy_cache[1]))
+            self._strategy_cache = (ver, new)
+            if moved:   # per-division caches (masks, pinned GT strips) belong to the old boundaries
+                self._strip_cache.clear(); self._mask_cache.clear(); self._bmask_cache.clear()
+                self.balance_log.append((self.iteration, [list(st.division_pos) for st in new],
+                                         [list(st.gpu_ids) for st in new]))
         strategies = self._strategy_cache[1]
         settings = [c.settings(p.active_sh_degree) for c in self.dcams]
         # "Asynchronously load ground-truth image to GPU" (loss_distribution.py:2399): the strips this rank needs are
@@ -354,11 +377,45 @@ class Trainer:
         self._mark("b4 backward (rest)")
         self._collectors, self._strategies = collectors, strategies
         self._counts = dict(Vp=Vp, P_local=Pl)
+        self.iteration += 1
+        self._feed_back_times(strategies, collectors)
+        self._mark("t time feedback")
         if resident:
             return None
         self._loss_host.copy_(loss_sum.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self._loss_host[0])
+
+    def _feed_back_times(self, strategies, collectors):
+        """finish_strategy_final (workload_division.py:944-998) + the time all-gather (utils/general_utils.py:249-269):
+        every rank contributes the render time of each camera it rendered a strip of; the per-row cost heuristic is
+        rebuilt from them and the NEXT step's strips move.  Only where the reference's gate enables it (more than one
+        rank, and not when whole <= 1080p images can be handed out)."""
+        import torch.distributed as dist
+        from .division import running_time_of
+        B = len(strategies)
+        if not (self.load_balance and self.world > 1 and
+                heuristics_update_enabled(self.iteration, self.world, B, self.H, self.W)):
+            return
+        mine = [-1.0] * B
+        rows = [(st.local_rows()[1] - st.local_rows()[0]) if st.local_rows() is not None else 0 for st in strategies]
+        if self._n_renders == 1 and sum(1 for r in rows if r) > 1:
+            # one batched render served all local strips: its time is apportioned by strip height (the reference times
+            # every camera's render separately, render_final __init__.py:1217-1288)
+            t = running_time_of(collectors[0])
+            for k, r in enumerate(rows):
+                if r:
+                    mine[k] = t * r / sum(rows)
+        else:
+            for k, r in enumerate(rows):
+                if r:
+                    c = collectors[k] if "forward_render_time" in collectors[k] else collectors[0]
+                    mine[k] = running_time_of(c)
+        loc = torch.tensor(mine, dtype=torch.float32, device=self.device)
+        allt = torch.empty((self.world * B,), dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(allt, loc, group=self.group)
+        times = allt.reshape(self.world, B).cpu().tolist()       # gpu_camera_running_time[gpu][camera]
+        finish_strategy(self.history, strategies, times, self.iteration, self.world, self.H, self.W, self.heuristic_decay)
 
     def last_info(self):
         """Realised sizes of the last step on this rank: V visible, V' splats rendered, R instances."""

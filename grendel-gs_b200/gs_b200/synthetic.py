@@ -94,6 +94,29 @@ def make_scene(n, width, height, fovx_deg=60.0, seed=0, radius_px=6.0):
     return dict(means3D=means3D, scales=scales, rotations=rotations, opacities=opacities, shs=shs)
 
 
+SHARD_CHUNK = 1 << 20
+
+
+def make_scene_shard(n, lo, hi, width, height, fovx_deg=60.0, seed=0, radius_px=6.0):
+    """Gaussians [lo, hi) of an n-Gaussian scene WITHOUT generating the rest: the scene is defined chunk by chunk
+    (SHARD_CHUNK Gaussians per chunk, each from its own generator seeded (seed, chunk)), so every rank of a large
+    configuration (c4: 40 M Gaussians = 9.4 GB of parameters) builds only its own shard, and the union over ranks is the
+    same scene for every world size.  Same distributions as make_scene (a different sample: make_scene draws the whole
+    scene from one stream)."""
+    parts = []
+    for c in range(lo // SHARD_CHUNK, (max(hi, lo + 1) - 1) // SHARD_CHUNK + 1):
+        c0 = c * SHARD_CHUNK
+        m = min(SHARD_CHUNK, n - c0)
+        if m <= 0:
+            break
+        sc = make_scene(m, width, height, fovx_deg, seed=(seed, c), radius_px=radius_px)
+        a, b = max(lo, c0) - c0, min(hi, c0 + m) - c0
+        parts.append({k: v[a:b] for k, v in sc.items()})
+    if not parts:
+        return {k: v[:0] for k, v in make_scene(1, width, height, fovx_deg, seed=(seed, 0), radius_px=radius_px).items()}
+    return {k: np.concatenate([q[k] for q in parts]) for k in parts[0]}
+
+
 def make_gt_image(width, height, seed=1):
     """uint8 (3,H,W) ground truth, as the reference keeps GT on the host (scene/cameras.py:66)."""
     rng = np.random.default_rng(seed)

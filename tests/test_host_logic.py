@@ -97,6 +97,24 @@ def test_finish_strategy_gate_follows_the_reference():
     assert division.start_strategy([3], hist, 2, 0)[0][0].division_pos[1] < st[0].division_pos[1]
 
 
+def test_feedback_loop_balances_an_uneven_scene():
+    """The loop Trainer.step closes (start_strategy -> measured times -> finish_strategy): with a fixed, uneven true
+    cost per tile row (the lower third of the image 5x as expensive), the strips move until every rank's time is
+    within ~one row of the mean, and stay there."""
+    world, tile_y = 4, 135
+    true = np.ones(tile_y); true[90:] = 5.0
+    hist = division.StrategyHistory([0], tile_y, world)
+    spread = []
+    for it in range(1, 12):
+        st, _ = division.start_strategy([0], hist, world, 0)
+        pos = st[0].division_pos
+        t = [[float(true[pos[g]:pos[g + 1]].sum())] for g in range(world)]
+        spread.append(max(x[0] for x in t) / (sum(x[0] for x in t) / world))
+        assert division.finish_strategy(hist, st, t, iteration=it, world_size=world, image_height=2160, image_width=3840)
+    assert spread[0] > 2.0                      # uniform strips: the rank with the expensive rows takes > 2x the mean
+    assert max(spread[3:]) < 1.1, spread        # balanced after a few iterations (one 5x row = 0.06 of a rank's share)
+
+
 def test_local_sampling_gives_whole_images():
     hist = division.StrategyHistory([0, 1, 2, 3], 30, 2)
     strategies, tasks = division.start_strategy([0, 1, 2, 3], hist, 2, 1, local_sampling=True)
