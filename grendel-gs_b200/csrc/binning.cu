@@ -27,19 +27,13 @@
 //   r1 = (c', opacity, thr, red)     thr = ln(1/(255*opacity)) - margin: power < thr  =>  alpha < 1/255
 //   r2 = (green, blue, ex, ey)       half extents of the bounding box of {power >= thr} (+0.5 px slack),
 //                                    used by the blend kernels to cull splats per 4x4 / 8x4 pixel block
-__global__ void __launch_bounds__(BIN_THREADS)
-k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const float *__restrict__ conic_opacity,
-              const float *__restrict__ rgb, const float *__restrict__ depths, const int32_t *__restrict__ radii,
-              const uint8_t *__restrict__ compute_locally, uint32_t *__restrict__ touched,
-              uint32_t *__restrict__ depth_key, uint32_t *__restrict__ index, float *__restrict__ rec, int no_cull,
-              const GsViews views) {
-    const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
-    if (i >= P) return;
+GS_D uint32_t count_local_tiles(int i, int W, int H, const float *__restrict__ means2D, const int32_t *__restrict__ radii,
+                                const uint8_t *__restrict__ compute_locally, const GsViews &views) {
     const int gx = (W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
     const int r = radii[i];
     uint32_t n = 0;
-    const float2 m = *reinterpret_cast<const float2 *>(means2D + 2 * i);
     if (r > 0) {
+        const float2 m = *reinterpret_cast<const float2 *>(means2D + 2 * i);
         int x0, y0, x1, y1;
         gs_get_rect(m.x, m.y, r, gx, gy, x0, y0, x1, y1);
         const uint8_t *mask = compute_locally + (size_t)gs_view_of(views, i) * views.T;
@@ -48,6 +42,27 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
             for (int x = x0; x < x1; x++) n += row[x] ? 1u : 0u;
         }
     }
+    return n;
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const float *__restrict__ conic_opacity,
+              const float *__restrict__ rgb, const float *__restrict__ depths, const int32_t *__restrict__ radii,
+              const uint8_t *__restrict__ compute_locally, uint32_t *__restrict__ touched,
+              uint32_t *__restrict__ depth_key, uint32_t *__restrict__ index, float *__restrict__ rec, int no_cull,
+              unsigned long long *__restrict__ total64, const GsViews views) {
+    const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    const bool valid = i < P;
+    // 64-bit instance total beside the 32-bit scan: a batch whose total reaches 2^32 would wrap the scan and pass the
+    // R < 2^31 check with corrupted offsets (one atomic per warp)
+    const uint32_t my_n = valid ? count_local_tiles(i, W, H, means2D, radii, compute_locally, views) : 0u;
+    {
+        const uint32_t wsum = __reduce_add_sync(0xffffffffu, my_n);   // <= 32 * T: no overflow
+        if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(total64, (unsigned long long)wsum);
+    }
+    if (!valid) return;
+    const uint32_t n = my_n;
+    const float2 m = *reinterpret_cast<const float2 *>(means2D + 2 * i);
     touched[i] = n;
     depth_key[i] = n > 0 ? __float_as_uint(depths[i]) : 0xffffffffu;  // depths are > 0.2: bits sort like values
     index[i] = (uint32_t)i;
@@ -181,13 +196,15 @@ extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start,
     uint32_t *touched = (uint32_t *)base, *dkey = (uint32_t *)(base + stride), *dkey_sorted = (uint32_t *)(base + 2 * stride),
              *index = (uint32_t *)(base + 3 * stride), *touched_sorted = (uint32_t *)(base + 4 * stride);
     void *cub_temp = base + 5 * stride;
-    size_t cub_bytes = temp_bytes - 5 * stride;
+    size_t cub_bytes = count_cub_bytes(P);
+    unsigned long long *total64 = (unsigned long long *)(base + 5 * stride + cub_bytes);  // the last 256 bytes of temp
+    GS_CUDA_TRY(cudaMemsetAsync(total64, 0, sizeof(unsigned long long), stream));
     const int grid = (P + BIN_THREADS - 1) / BIN_THREADS;
     {
         GsStageTimer timer(GS_STAGE_COUNT_TILES, stream);
         k_count_tiles<<<grid, BIN_THREADS, 0, stream>>>(P, image_width, image_height, means2D, conic_opacity, rgb, depths,
                                                         radii, compute_locally, touched, dkey, index, rec,
-                                                        (g_gs_debug_flags & GS_DEBUG_NO_BLOCK_CULL) ? 1 : 0, views);
+                                                        (g_gs_debug_flags & GS_DEBUG_NO_BLOCK_CULL) ? 1 : 0, total64, views);
         GS_LAUNCH_CHECK();
     }
     {
@@ -200,10 +217,15 @@ extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start,
         GS_LAUNCH_CHECK();
         GS_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_temp, cub_bytes, touched_sorted, offsets, P, stream));
     }
-    uint32_t last = 0;
-    GS_CUDA_TRY(cudaMemcpyAsync(&last, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    unsigned long long total = 0;
+    GS_CUDA_TRY(cudaMemcpyAsync(&total, total64, sizeof(total), cudaMemcpyDeviceToHost, stream));
     GS_CUDA_TRY(cudaStreamSynchronize(stream));
-    *R_host = (int64_t)last;
+    if (total >= (1ull << 31)) {  // the 32-bit scan (and the int32 instance indices downstream) cannot hold it
+        gs_set_error("gs_render_count: %llu splat-tile instances in one call (limit 2^31 - 1): render fewer views per call",
+                     total);
+        return GS_EINVAL;
+    }
+    *R_host = (int64_t)total;
     return GS_OK;
 }
 

@@ -692,3 +692,271 @@ extern "C" int gs_sparse_grad_unpack(int P, const uint8_t *mask, const int32_t *
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
+
+// ---- direct-placement exchange (round 2) ---------------------------------------------------------------------------
+// The first peer-memory exchange still materialised a dense [destination][camera][splat] flag array, a W*B*P-element
+// scan (64 MB of positions at W = B = 8), a row-major staging layout and an unpack pass on the receiver; at 8 GPUs its
+// pack kernel alone took 0.54 ms for 49 MB -- ten times the NVLink wire time.  Here:
+//   * routing is recomputed from (means2D, radius) wherever it is needed (12 B per splat) instead of being stored;
+//   * positions come from per-CTA hit counts ([destination][camera][block of 256 splats]: W*B*P/256 integers, scanned
+//     in microseconds) plus a ballot prefix inside the CTA -- the order is still the reference's (per destination:
+//     cameras in batch order, splats in index order; per receiver: sources in rank order);
+//   * the pack kernel stores every field straight into its FINAL place in the destination rank's structure-of-arrays
+//     receive region (means2D | rgb | conic_opacity | radii | depths, `cap` rows each), i.e. the tensors the render reads:
+//     no staging rows, no unpack;
+//   * backward, the source PULLS: the receiver's render backward leaves its gradients in its own peer-visible region
+//     (d means2D | d rgb | d conic_opacity) and the owner of a splat loads the rows of its (at most few) destinations over
+//     NVLink and sums them -- no pack kernel on the receiver, no atomics.
+#define XR_NB(P) (((P) + DT_THREADS - 1) / DT_THREADS)
+
+struct XrGeom {           // what a rank needs to recompute "which strip owners does splat i of camera k reach"
+    const float *m2[XB];
+    const int32_t *rad[XB];
+    XRows rows;
+    int B, P, Wr, W, H;
+};
+struct XrPeers { char *base[XW]; int32_t row0[XW * XB]; long long cap; };  // row0[j*B+k]: my first row in rank j's camera k
+
+GS_D uint32_t xr_hits(const XrGeom &g, int k, int i, bool valid) {
+    if (!valid) return 0u;
+    const int r = g.rad[k][i];
+    if (r <= 0) return 0u;
+    const int gx = (g.W + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (g.H + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
+    int x0, y0, x1, y1;
+    const float2 m = *reinterpret_cast<const float2 *>(g.m2[k] + 2 * (size_t)i);
+    gs_get_rect(m.x, m.y, r, gx, gy, x0, y0, x1, y1);
+    uint32_t h = 0u;
+    if (x1 > x0)
+        for (int j = 0; j < g.Wr; j++)
+            if (max(y0, (int)g.rows.lo[k * XW + j]) < min(y1, (int)g.rows.hi[k * XW + j])) h |= 1u << j;
+    return h;
+}
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_xr_count(XrGeom g, int32_t *__restrict__ blkcnt) {
+    __shared__ int32_t s_cnt[DT_THREADS / 32][XW];
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t h = xr_hits(g, k, i, i < g.P);
+    for (int j = 0; j < g.Wr; j++) {
+        const int c = __popc(__ballot_sync(0xffffffffu, (h >> j) & 1u));
+        if (lane == 0) s_cnt[warp][j] = c;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < g.Wr) {
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < DT_THREADS / 32; w++) c += s_cnt[w][threadIdx.x];
+        blkcnt[((size_t)threadIdx.x * g.B + k) * gridDim.x + blockIdx.x] = c;
+    }
+}
+
+__global__ void k_xr_totals(int n_cols, int NB, const int32_t *__restrict__ blkcnt, const int32_t *__restrict__ blkbase,
+                            int32_t *__restrict__ counts) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;  // column = j*B + k
+    if (c >= n_cols) return;
+    const size_t last = (size_t)(c + 1) * NB - 1;
+    counts[c] = blkbase[last] + blkcnt[last] - blkbase[(size_t)c * NB];
+}
+
+// per-CTA position of this thread's row for destination j: rows of the CTA's hits in thread order
+struct XrRank { int32_t warp_base[DT_THREADS / 32]; };
+GS_D int xr_local_rank(uint32_t h, int j, int warp, int lane, int32_t (*s_wcnt)[XW]) {
+    const uint32_t b = __ballot_sync(0xffffffffu, (h >> j) & 1u);
+    int r = __popc(b & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; w++) r += s_wcnt[w][j];
+    return r;
+}
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_xr_pack(XrGeom g, XIn in, const int32_t *__restrict__ blkbase, XrPeers peers) {
+    __shared__ int32_t s_wcnt[DT_THREADS / 32][XW];
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool valid = i < g.P;
+    const uint32_t h = xr_hits(g, k, i, valid);
+    uint32_t any = __reduce_or_sync(0xffffffffu, h);
+    for (int j = 0; j < g.Wr; j++) {
+        const int c = __popc(__ballot_sync(0xffffffffu, (h >> j) & 1u));
+        if (lane == 0) s_wcnt[warp][j] = c;
+    }
+    __syncthreads();
+    if (any == 0u) return;
+    float2 m = make_float2(0.f, 0.f);
+    float4 co = make_float4(0.f, 0.f, 0.f, 0.f);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, dep = 0.f;
+    int rad = 0;
+    if (h) {
+        m = *reinterpret_cast<const float2 *>(in.m2[k] + 2 * (size_t)i);
+        co = *reinterpret_cast<const float4 *>(in.co[k] + 4 * (size_t)i);
+        r0 = in.rgb[k][3 * (size_t)i]; r1 = in.rgb[k][3 * (size_t)i + 1]; r2 = in.rgb[k][3 * (size_t)i + 2];
+        rad = in.rad[k][i]; dep = in.dep[k][i];
+    }
+    const long long cap = peers.cap;
+    while (any) {
+        const int j = __ffs(any) - 1;
+        any &= any - 1u;
+        const int lr = xr_local_rank(h, j, warp, lane, s_wcnt);
+        if (!((h >> j) & 1u)) continue;
+        const size_t col = (size_t)j * g.B + k;
+        const long long row = (long long)peers.row0[col] + (blkbase[col * gridDim.x + blockIdx.x] - blkbase[col * gridDim.x]) + lr;
+        float *b = reinterpret_cast<float *>(peers.base[j]);
+        *reinterpret_cast<float2 *>(b + 2 * row) = m;
+        float *q = b + 2 * cap + 3 * row;
+        q[0] = r0; q[1] = r1; q[2] = r2;
+        *reinterpret_cast<float4 *>(b + 5 * cap + 4 * row) = co;
+        reinterpret_cast<int32_t *>(b + 9 * cap)[row] = rad;
+        (b + 10 * cap)[row] = dep;
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_xr_pull_grad(XrGeom g, const int32_t *__restrict__ blkbase, XrPeers peers, XOut out) {
+    __shared__ int32_t s_wcnt[DT_THREADS / 32][XW];
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool valid = i < g.P;
+    const uint32_t h = xr_hits(g, k, i, valid);
+    uint32_t any = __reduce_or_sync(0xffffffffu, h);
+    for (int j = 0; j < g.Wr; j++) {
+        const int c = __popc(__ballot_sync(0xffffffffu, (h >> j) & 1u));
+        if (lane == 0) s_wcnt[warp][j] = c;
+    }
+    __syncthreads();
+    float2 dm = make_float2(0.f, 0.f);
+    float4 dco = make_float4(0.f, 0.f, 0.f, 0.f);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    const long long cap = peers.cap;
+    while (any) {   // ascending destination rank: the summation order of the reference's index_add over received blocks
+        const int j = __ffs(any) - 1;
+        any &= any - 1u;
+        const int lr = xr_local_rank(h, j, warp, lane, s_wcnt);
+        if (!((h >> j) & 1u)) continue;
+        const size_t col = (size_t)j * g.B + k;
+        const long long row = (long long)peers.row0[col] + (blkbase[col * gridDim.x + blockIdx.x] - blkbase[col * gridDim.x]) + lr;
+        const float *b = reinterpret_cast<const float *>(peers.base[j]);
+        const float2 a = *reinterpret_cast<const float2 *>(b + 2 * row);
+        const float *q = b + 2 * cap + 3 * row;
+        const float4 c = *reinterpret_cast<const float4 *>(b + 5 * cap + 4 * row);
+        dm.x += a.x; dm.y += a.y;
+        d0 += q[0]; d1 += q[1]; d2 += q[2];
+        dco.x += c.x; dco.y += c.y; dco.z += c.z; dco.w += c.w;
+    }
+    if (valid) {
+        *reinterpret_cast<float2 *>(out.m2[k] + 2 * (size_t)i) = dm;
+        float *q = out.rgb[k] + 3 * (size_t)i;
+        q[0] = d0; q[1] = d1; q[2] = d2;
+        *reinterpret_cast<float4 *>(out.co[k] + 4 * (size_t)i) = dco;
+    }
+}
+
+static int xr_geom(XrGeom &g, int B, int P, int W, int H, int Wimg, const void *const *m2, const void *const *rad,
+                   const int32_t *row_lo, const int32_t *row_hi) {
+    GS_REQUIRE(B > 0 && B <= XB && W > 0 && W <= XW && P >= 0, "sizes (<= 16 cameras, <= 16 ranks)");
+    GS_REQUIRE(H > 0 && Wimg > 0 && m2 && rad && row_lo && row_hi, "geometry");
+    g.B = B; g.P = P; g.Wr = W; g.W = Wimg; g.H = H;
+    for (int k = 0; k < XB; k++) {
+        g.m2[k] = k < B ? (const float *)m2[k] : nullptr;
+        g.rad[k] = k < B ? (const int32_t *)rad[k] : nullptr;
+        for (int j = 0; j < XW; j++) {
+            const bool v = k < B && j < W;
+            g.rows.lo[k * XW + j] = v ? (int16_t)row_lo[k * W + j] : 0;
+            g.rows.hi[k * XW + j] = v ? (int16_t)row_hi[k * W + j] : 0;
+        }
+    }
+    return GS_OK;
+}
+
+static int xr_peers(XrPeers &p, int B, int W, void *const *bases, const int32_t *row0, long long cap) {
+    GS_REQUIRE(bases && row0 && cap > 0 && (cap & 3) == 0, "peer tables (capacity must be a multiple of 4 rows)");
+    p.cap = cap;
+    for (int j = 0; j < XW; j++) {
+        p.base[j] = j < W ? (char *)bases[j] : nullptr;
+        GS_REQUIRE(j >= W || p.base[j] != nullptr, "null peer buffer");
+    }
+    for (int c = 0; c < XW * XB; c++) p.row0[c] = c < W * B ? row0[c] : 0;
+    return GS_OK;
+}
+
+extern "C" size_t gs_xr_temp_bytes(int B, int P, int W) {
+    size_t b = 0;
+    const long long n = (long long)(B > 0 ? B : 1) * (W > 0 ? W : 1) * XR_NB(P > 0 ? P : 1);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n);
+    return align_up(b, 256) + 256;
+}
+
+// blkcnt, blkbase: (W*B*ceil(P/256)) int32 each, laid out [destination j][camera k][block]; counts: (W*B) int32 [j][k].
+extern "C" int gs_xr_count(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                           const void *const *radii_ptrs_host, const int32_t *row_lo_host, const int32_t *row_hi_host,
+                           int32_t *blkcnt, int32_t *blkbase, int32_t *counts, void *temp, size_t temp_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    XrGeom g;
+    int rc = xr_geom(g, B, P, W, image_height, image_width, means2D_ptrs_host, radii_ptrs_host, row_lo_host, row_hi_host);
+    if (rc != GS_OK) return rc;
+    GS_REQUIRE(counts != nullptr, "counts");
+    if (P == 0) {
+        GS_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B * W, stream));
+        return GS_OK;
+    }
+    GS_REQUIRE(blkcnt && blkbase && temp, "null pointer");
+    const int NB = XR_NB(P);
+    GsStageTimer timer(GS_STAGE_LOCAL2J, stream);
+    k_xr_count<<<dim3(NB, B), DT_THREADS, 0, stream>>>(g, blkcnt);
+    GS_LAUNCH_CHECK();
+    GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, blkcnt, blkbase, W * B * NB, stream));
+    k_xr_totals<<<(B * W + 63) / 64, 64, 0, stream>>>(B * W, NB, blkcnt, blkbase, counts);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+// peer_recv_ptrs_host[j]: rank j's receive region (11 * cap floats: means2D | rgb | conic_opacity | radii | depths) as
+// mapped into this process; dst_row0_host[j*B+k]: first row of THIS rank's block inside camera k of rank j's arrays.
+extern "C" int gs_xr_pack(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                          const void *const *rgb_ptrs_host, const void *const *conic_opacity_ptrs_host,
+                          const void *const *radii_ptrs_host, const void *const *depths_ptrs_host,
+                          const int32_t *row_lo_host, const int32_t *row_hi_host, const int32_t *blkbase,
+                          void *const *peer_recv_ptrs_host, const int32_t *dst_row0_host, long long cap_rows, void *stream) {
+    XrGeom g;
+    int rc = xr_geom(g, B, P, W, image_height, image_width, means2D_ptrs_host, radii_ptrs_host, row_lo_host, row_hi_host);
+    if (rc != GS_OK) return rc;
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(rgb_ptrs_host && conic_opacity_ptrs_host && depths_ptrs_host && blkbase, "null pointer");
+    XrPeers peers;
+    rc = xr_peers(peers, B, W, peer_recv_ptrs_host, dst_row0_host, cap_rows);
+    if (rc != GS_OK) return rc;
+    XIn in;
+    fill_in(in, B, means2D_ptrs_host, rgb_ptrs_host, conic_opacity_ptrs_host, radii_ptrs_host, depths_ptrs_host);
+    GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
+    k_xr_pack<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+// peer_grad_ptrs_host[j]: rank j's gradient region (9 * cap floats: d means2D | d rgb | d conic_opacity); the outputs
+// are the (B,P,.) gradients of this rank's projected splats: the sum over the destinations each splat was sent to.
+extern "C" int gs_xr_pull_grad(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                               const void *const *radii_ptrs_host, const int32_t *row_lo_host, const int32_t *row_hi_host,
+                               const int32_t *blkbase, void *const *peer_grad_ptrs_host, const int32_t *dst_row0_host,
+                               long long cap_rows, void *const *d_means2D_ptrs_host, void *const *d_rgb_ptrs_host,
+                               void *const *d_conic_opacity_ptrs_host, void *stream) {
+    XrGeom g;
+    int rc = xr_geom(g, B, P, W, image_height, image_width, means2D_ptrs_host, radii_ptrs_host, row_lo_host, row_hi_host);
+    if (rc != GS_OK) return rc;
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(blkbase && d_means2D_ptrs_host && d_rgb_ptrs_host && d_conic_opacity_ptrs_host, "null pointer");
+    XrPeers peers;
+    rc = xr_peers(peers, B, W, peer_grad_ptrs_host, dst_row0_host, cap_rows);
+    if (rc != GS_OK) return rc;
+    XOut out;
+    for (int k = 0; k < XB; k++) {
+        out.m2[k] = k < B ? (float *)d_means2D_ptrs_host[k] : nullptr;
+        out.rgb[k] = k < B ? (float *)d_rgb_ptrs_host[k] : nullptr;
+        out.co[k] = k < B ? (float *)d_conic_opacity_ptrs_host[k] : nullptr;
+        out.rad[k] = nullptr; out.dep[k] = nullptr;
+    }
+    GsStageTimer timer(GS_STAGE_UNPACK, (cudaStream_t)stream);
+    k_xr_pull_grad<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, blkbase, peers, out);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

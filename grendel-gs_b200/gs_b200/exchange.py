@@ -21,6 +21,11 @@ import torch.distributed as dist
 from . import _lib, ops
 
 ROW, GROW = 11, 9
+MAX_CAMERAS, MAX_RANKS, MAX_SEGMENTS = 16, 16, 128   # XB, XW, XSEG of csrc/distribute.cu
+# "direct": direct-placement kernels over peer memory (default when peer buffers exist); "rows": round 1's row-staged
+# peer path (pack rows -> unpack), kept for A/B (GS_B200_EXCHANGE_MODE=rows)
+import os as _os
+MODE = _os.environ.get("GS_B200_EXCHANGE_MODE", "direct")
 TRACE = None   # diagnostics: callable(name) that synchronises and charges the time since the last mark (pipeline._mark)
 
 
@@ -140,8 +145,10 @@ class PeerBuffers:
     Collective: every rank of `group` must construct it at the same point (handles travel by all_gather)."""
 
     def __init__(self, world, me, cap_rows, device, group=None):
-        self.world, self.me, self.cap_rows, self.group = world, me, int(cap_rows), group
+        self.world, self.me, self.cap_rows, self.group = world, me, (int(cap_rows) + 3) // 4 * 4, group
+        self.device = device
         self._owned, self._opened = [], []
+        self._views = None
         self.token = torch.zeros((1,), dtype=torch.float32, device=device)
         # every local step that can fail is followed by an agreement (all-reduce MIN), so that either all ranks go on
         # or all ranks raise -- never a rank stuck alone in a collective
@@ -183,8 +190,32 @@ class PeerBuffers:
 
     def barrier(self):
         """Stream-ordered: completes on this rank once every rank's stream reached the same call (a 4-byte all-reduce;
-        the host does not block)."""
+        the host does not block).
+
+        Buffer-reuse invariant: a peer writes into this rank's recv / grad buffer only from its pack kernels,
+        and it launches those only after gather_counts() of the SAME exchange -- an all-gather on the same stream that
+        this rank joins after its unpack / scatter of the previous exchange were enqueued.  So the next remote write is
+        ordered after this rank's last read as long as (a) every exchange starts with gather_counts and (b) exchange,
+        consumers and collectives share one stream.  A caller that caches counts or moves the consumers to another stream
+        must call barrier() after its consumers instead."""
         dist.all_reduce(self.token, op=dist.ReduceOp.MAX, group=self.group)   # MAX of zeros: the value never grows
+
+    def views(self):
+        """This rank's own buffers as torch tensors in the structure-of-arrays layout of the direct-placement exchange
+        (csrc/distribute.cu "xr"): ((means2D (cap,2), rgb (cap,3), conic_opacity (cap,4), radii (cap) int32, depths (cap)),
+        (d means2D, d rgb, d conic_opacity)) -- zero-copy views of the peer-visible memory."""
+        if self._views is None:
+            cap, dev = self.cap_rows, self.device
+            r, g = self.recv[self.me], self.grad[self.me]
+            f = lambda base, off, shape: _wrap(base + 4 * off * cap, shape, "<f4", dev)
+            self._views = ((f(r, 0, (cap, 2)), f(r, 2, (cap, 3)), f(r, 5, (cap, 4)),
+                            _wrap(r + 4 * 9 * cap, (cap,), "<i4", dev), f(r, 10, (cap,))),
+                           (f(g, 0, (cap, 2)), f(g, 2, (cap, 3)), f(g, 5, (cap, 4))))
+        return self._views
+
+    def fits_direct(self, cnt):
+        """Do every rank's received rows (all cameras) fit the structure-of-arrays regions?  Same answer on every rank."""
+        return int(np.asarray(cnt, dtype=np.int64).sum(axis=(0, 1)).max()) <= self.cap_rows
 
     def fits(self, cnt):
         """Do all ranks' receive and send totals of this step fit the buffers?  Same answer on every rank."""
@@ -199,6 +230,30 @@ class PeerBuffers:
                 except _lib.GsError:
                     pass
         self._opened, self._owned = [], []
+
+
+class _DevMem:
+    """__cuda_array_interface__ holder: lets torch view device memory it did not allocate (the IPC-exported buffers)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _wrap(ptr, shape, typestr, device):
+    return torch.as_tensor(_DevMem(ptr, shape, typestr), device=device)
+
+
+def direct_rows(cnt, me):
+    """Direct-placement layout from the all-gathered counts cnt[i][k][j]:
+    -> (dst_row0[j][k] = first row of MY block inside camera k of rank j's arrays, my view_start (B+1))."""
+    c = np.asarray(cnt, dtype=np.int64)                        # (W, B, W)
+    per_cam = c.sum(axis=0)                                    # [k][j]: rows of camera k on rank j
+    view_start = _excl(per_cam, axis=0)                        # [k][j]
+    before_me = c[:me].sum(axis=0)                             # [k][j]: rows of ranks < me
+    row0 = (view_start + before_me).T                          # [j][k]
+    mine = np.concatenate([view_start[:, me], [per_cam[:, me].sum()]])
+    return row0.reshape(-1).tolist(), [int(v) for v in mine]
 
 
 def peer_row_deltas(cnt, me):
@@ -314,6 +369,56 @@ class _ExchangeSplats(torch.autograd.Function):
         return None, d_m2, d_rgb, d_co
 
 
+class _ExchangeSplatsDirect(torch.autograd.Function):
+    """Same contract as _ExchangeSplats over the direct-placement kernels: the pack kernel stores every field into its final
+    row of the destination's arrays (the outputs ARE views of this rank's peer-visible receive region: no unpack), and the
+    backward pulls the gradient rows from the destinations' gradient regions."""
+
+    @staticmethod
+    def forward(ctx, state, m2, rgb, co):
+        B, P, W, peer = state["B"], state["P"], state["W"], state["peer"]
+        m2, rgb, co = m2.contiguous(), rgb.contiguous(), co.contiguous()
+        s = ops._stream()
+        _lib.call("gs_xr_pack", B, P, W, state["H"], state["Wimg"], _slab_ptrs(state["m2d"], B), _slab_ptrs(rgb, B),
+                  _slab_ptrs(co, B), _slab_ptrs(state["radii"], B), _slab_ptrs(state["depths"], B), state["lo"], state["hi"],
+                  state["blkbase"].data_ptr(), (C.c_void_p * W)(*peer.recv), state["row0"], C.c_longlong(peer.cap_rows), s)
+        _t("x3 pack")
+        peer.barrier()
+        _t("x4 all_to_all")
+        N = state["view_start"][B]
+        (v_m2, v_rgb, v_co, v_rad, v_dep), _ = peer.views()
+        om2, orgb, oco, orad, odep = v_m2[:N], v_rgb[:N], v_co[:N], v_rad[:N], v_dep[:N]
+        ctx.state = state
+        ctx.mark_non_differentiable(orad, odep)
+        return om2, orgb, oco, orad, odep
+
+    @staticmethod
+    def backward(ctx, g_m2, g_rgb, g_co, *_unused):
+        state = ctx.state
+        B, P, W, peer = state["B"], state["P"], state["W"], state["peer"]
+        dev = state["radii"].device
+        s = ops._stream()
+        N = state["view_start"][B]
+        _t("b1 loss+render backward")
+        _, (v_dm2, v_drgb, v_dco) = peer.views()
+        for view, g in ((v_dm2, g_m2), (v_drgb, g_rgb), (v_dco, g_co)):   # into the peer-visible gradient region
+            if g is None:
+                view[:N].zero_()
+            else:
+                view[:N].copy_(g)
+        _t("b2 pack_grad")
+        peer.barrier()
+        _t("b3 all_to_all")
+        d_m2 = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
+        d_co = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+        _lib.call("gs_xr_pull_grad", B, P, W, state["H"], state["Wimg"], _slab_ptrs(state["m2d"], B),
+                  _slab_ptrs(state["radii"], B), state["lo"], state["hi"], state["blkbase"].data_ptr(),
+                  (C.c_void_p * W)(*peer.grad), state["row0"], C.c_longlong(peer.cap_rows), _slab_ptrs(d_m2, B),
+                  _slab_ptrs(d_rgb, B), _slab_ptrs(d_co, B), s)
+        return None, d_m2, d_rgb, d_co
+
+
 def open_peer_buffers(world, me, cap_rows, device, group=None):
     """PeerBuffers if every rank of the group could allocate, export and map them, else None on ALL ranks (the
     exchange then uses all_to_all_single).  Collective."""
@@ -350,6 +455,11 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
     none if the rank renders no strip of it), and the all-gathered counts cnt[i][k][j] (the reference's
     gpui_to_gpuj_imgk_size)."""
     B, P = means2D.shape[0], means2D.shape[1]
+    # the kernels' static limits, checked HERE from values every rank shares (world, bsz, and below the all-gathered
+    # counts): a rank-local failure inside a C call between two collectives would leave the other ranks hanging
+    if world > MAX_RANKS or B > MAX_CAMERAS:
+        raise ValueError(f"exchange supports <= {MAX_RANKS} ranks and <= {MAX_CAMERAS} cameras per step "
+                         f"(got {world} ranks, {B} cameras): split the batch")
     dev = means2D.device
     H, Wimg = int(settings[0].image_height), int(settings[0].image_width)
     lo, hi = [0] * (B * world), [0] * (B * world)
@@ -359,6 +469,27 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
     radii = radii.to(torch.int32).contiguous()
     depths = depths.contiguous()
     m2d = means2D.detach().contiguous()
+    if peer is not None and MODE == "direct":
+        # direct placement: per-block hit counts instead of a dense flag array + W*B*P-element scan
+        nblk = max(world * B * ((max(P, 1) + 255) // 256), 1)
+        blkcnt = torch.empty((nblk,), dtype=torch.int32, device=dev)
+        blkbase = torch.empty((nblk,), dtype=torch.int32, device=dev)
+        counts = torch.empty((world, B), dtype=torch.int32, device=dev)   # [dest j][camera k]
+        tb = _lib.query("gs_xr_temp_bytes", B, P, world)
+        temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
+        lo_c, hi_c = _i32(lo), _i32(hi)
+        _lib.call("gs_xr_count", B, P, world, H, Wimg, _slab_ptrs(m2d, B), _slab_ptrs(radii, B), lo_c, hi_c,
+                  blkcnt.data_ptr(), blkbase.data_ptr(), counts.data_ptr(), temp.data_ptr(), tb, ops._stream())
+        _t("x1 route")
+        cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]
+        _t("x2 gather counts")
+        if peer.fits_direct(cnt):   # decided from the all-gathered counts: identical on all ranks
+            row0, view_start = direct_rows(cnt, me)
+            state = dict(group=group, radii=radii, depths=depths, m2d=m2d, blkbase=blkbase, B=B, P=P, W=world, H=H,
+                         Wimg=Wimg, lo=lo_c, hi=hi_c, row0=_i32(row0), view_start=view_start, peer=peer, cnt=cnt, me=me)
+            res = _ExchangeSplatsDirect.apply(state, means2D, rgb, conic_opacity)
+            return res, view_start, cnt
+        # does not fit the buffers this step: the row-staged path below (all_to_all_single) handles any size
     n = max(B * P * world, 1)
     flags = torch.empty((n,), dtype=torch.uint8, device=dev)
     gpos = torch.empty((n,), dtype=torch.int32, device=dev)
@@ -370,6 +501,10 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
     _t("x1 route")
     cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]
     _t("x2 gather counts")
+    nseg = int((np.asarray(cnt) > 0).sum(axis=(0, 1)).max())   # non-empty (source, camera) blocks of the busiest receiver
+    if nseg >= MAX_SEGMENTS:    # identical on every rank: all raise together
+        raise ValueError(f"exchange: a rank would receive {nseg} (source, camera) blocks, limit {MAX_SEGMENTS - 1}: "
+                         f"use fewer cameras per step")
     layout = Layout(cnt, me, [st.gpu_ids for st in strategies])
     view_start = [0]
     for n in layout.n_recv:

@@ -356,6 +356,32 @@ GS_API int gs_xchg_pack_grad_p2p(int nseg, const int32_t *seg_recv_start_host, c
                                  const void *const *d_conic_opacity_ptrs_host, void *const *seg_dst_ptrs_host,
                                  void *stream);
 
+/* ---- direct-placement exchange (csrc/distribute.cu, "xr"): same collective, same row order, but nothing is staged --
+ * gs_xr_count: per (destination rank j, camera k, block of 256 splats) hit counts + their exclusive scan + the (j,k)
+ * totals (the counts every rank all-gathers, gaussian_renderer/__init__.py:574-588).
+ * gs_xr_pack: every splat is stored field by field into its FINAL row of the destination rank's structure-of-arrays
+ * receive region (means2D | rgb | conic_opacity | radii | depths, cap_rows rows each; gs_peer_alloc'ed, 11*cap floats),
+ * i.e. straight into the tensors that rank's render reads -- no send rows, no unpack (replaces :590-607 and :631-658).
+ * gs_xr_pull_grad: the mirrored backward; the owner of a splat loads its gradient rows from the gradient regions
+ * (d means2D | d rgb | d conic_opacity, 9*cap floats) of the ranks it sent the splat to and sums them.
+ * row_lo/row_hi: (B*W) HOST ints as in gs_xchg_route; dst_row0_host[j*B+k]: first row of the calling rank's block inside
+ * camera k of rank j's arrays (from the all-gathered counts).  The caller orders pack -> consumers and the gradient
+ * writers -> pull across ranks (a stream-ordered barrier). */
+GS_API size_t gs_xr_temp_bytes(int B, int P, int W);
+GS_API int gs_xr_count(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                       const void *const *radii_ptrs_host, const int32_t *row_lo_host, const int32_t *row_hi_host,
+                       int32_t *blkcnt, int32_t *blkbase, int32_t *counts, void *temp, size_t temp_bytes, void *stream);
+GS_API int gs_xr_pack(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                      const void *const *rgb_ptrs_host, const void *const *conic_opacity_ptrs_host,
+                      const void *const *radii_ptrs_host, const void *const *depths_ptrs_host,
+                      const int32_t *row_lo_host, const int32_t *row_hi_host, const int32_t *blkbase,
+                      void *const *peer_recv_ptrs_host, const int32_t *dst_row0_host, long long cap_rows, void *stream);
+GS_API int gs_xr_pull_grad(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                           const void *const *radii_ptrs_host, const int32_t *row_lo_host, const int32_t *row_hi_host,
+                           const int32_t *blkbase, void *const *peer_grad_ptrs_host, const int32_t *dst_row0_host,
+                           long long cap_rows, void *const *d_means2D_ptrs_host, void *const *d_rgb_ptrs_host,
+                           void *const *d_conic_opacity_ptrs_host, void *stream);
+
 /* ---- sparse per-Gaussian gradient all-reduce staging (replicated Gaussians) ----------------------------------
  * /root/reference/scene/gaussian_model.py:1332-1391 (get_sparse_ids, sync_gradients_sparsely) and the
  * "fused_sparse" mode it leaves NotImplemented (:1438-1439).  mask[i] = _xyz.grad row i is non-zero; after an
