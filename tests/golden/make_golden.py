@@ -76,6 +76,21 @@ def main():
     loss.backward()
     np.savez(os.path.join(HERE, "loss.npz"), img=img.numpy(), gt_u8=gt_u8.numpy(), n_pix=n_pix, l1=l1.item(),
              ssim=ss.item(), loss=loss.item(), grad=x.grad.numpy())
+    # --- covariance: build_rotation / build_scaling_rotation / strip_symmetric (utils/general_utils.py:400-451) chained as
+    # build_covariance_from_scaling_rotation does (scene/gaussian_model.py:35-39).  The functions hard-code device="cuda";
+    # they are executed here from the reference's own source text with that one literal replaced by "cpu".
+    src = open(os.path.join(REF, "utils/general_utils.py")).read()
+    a, b = src.index("def strip_lowerdiag"), src.index("def safe_state")
+    ns = {"torch": torch}
+    exec(src[a:b].replace('device="cuda"', 'device="cpu"'), ns)
+    n = 300
+    scal = np.exp(rng.normal(-2.0, 1.0, (n, 3))).astype(np.float32)
+    rot = rng.normal(0, 1, (n, 4)).astype(np.float32)              # unnormalised, as the raw parameter
+    mod = 1.0
+    L = ns["build_scaling_rotation"](mod * torch.tensor(scal), torch.tensor(rot))
+    cov = ns["strip_symmetric"](L @ L.transpose(1, 2))
+    np.savez(os.path.join(HERE, "cov3d.npz"), scales=scal, rotations=rot, R=ns["build_rotation"](torch.tensor(rot)).numpy(),
+             cov6=cov.numpy())
     print("golden vectors written to", HERE)
 
 

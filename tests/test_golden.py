@@ -65,3 +65,31 @@ def test_loss_matches_reference_loss_utils():
     loss = 0.8 * l1 + 0.2 * (1 - ss)
     assert abs(loss - float(z["loss"])) < 1e-6
     np.testing.assert_allclose(grad, z["grad"], rtol=2e-3, atol=2e-9)
+
+
+def test_covariance_matches_reference_build_scaling_rotation():
+    """cov3d_from (oracle/gs_oracle.c) == strip_symmetric(L L^T), L = build_rotation(q) diag(s), executed from the
+    reference's own source (utils/general_utils.py:400-451; tests/golden/make_golden.py): pins the (w,x,y,z) convention,
+    the element order (xx, xy, xz, yy, yz, zz) and Sigma = R S S^T R^T."""
+    z = np.load(os.path.join(G, "cov3d.npz"))
+    n = z["scales"].shape[0]
+    q = z["rotations"].astype(np.float64)
+    q = (q / np.sqrt((q * q).sum(1, keepdims=True)))
+    cam = syn.make_camera(320, 200)
+    pts = np.tile(np.array([[0.0, 0.0, 5.0]]), (n, 1))          # all in front of the camera: every covariance is written
+    for dt in (np.float64, np.float32):
+        o = Oracle(dt)
+        pre = o.preprocess_forward(pts, z["scales"], q, np.zeros((n, 16, 3)), np.full((n, 1), 0.5), cam)
+        assert (pre["radii"] > 0).all()
+        # the golden itself is fp32 (off-diagonal elements cancel): the bar is relative to each covariance's largest element
+        err = np.abs(pre["cov3D"] - z["cov6"]) / np.abs(z["cov6"]).max(axis=1, keepdims=True)
+        assert err.max() < (2e-6 if dt == np.float64 else 4e-6), err.max()
+    # the rotation matrix itself, rebuilt from the covariance of unit scales along one axis at a time
+    R = z["R"].astype(np.float64)
+    for axis in range(3):
+        s = np.full((n, 3), 1e-3); s[:, axis] = 1.0
+        pre = Oracle(np.float64).preprocess_forward(pts, s, q, np.zeros((n, 16, 3)), np.full((n, 1), 0.5), cam)
+        c = pre["cov3D"]
+        full = np.stack([c[:, [0, 1, 2]], c[:, [1, 3, 4]], c[:, [2, 4, 5]]], 1)
+        col = R[:, :, axis]
+        np.testing.assert_allclose(full, col[:, :, None] * col[:, None, :], rtol=0, atol=3e-6)
