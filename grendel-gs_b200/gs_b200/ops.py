@@ -311,7 +311,20 @@ class _RenderGaussians(torch.autograd.Function):
 
 def render_gaussians(means2D, conic_opacity, rgb, depths, radii, compute_locally, raster_settings, cuda_args=None,
                      extended_compute_locally=None):
-    """-> (image (3,H,W) with non-local tiles exactly 0, n_render, n_consider, n_contrib)."""
+    """-> (image (3,H,W) with non-local tiles exactly 0, n_render, n_consider, n_contrib).
+
+    extended_compute_locally: the live path passes None (workload_division.py:802-803); the legacy render()
+    (gaussian_renderer/__init__.py:458-507) passes the local tile region dilated by one tile
+    (workload_division.py:142-156, 435-448).  What the fork's CUDA code did with it is not observable (its source is an
+    absent submodule) and every in-tree consumer of the result requires the image to be exactly zero outside
+    compute_locally (loss_distribution.py:1875), so the mask is validated -- a (TILE_Y, TILE_X) boolean mask that covers
+    compute_locally -- and the blend stays confined to compute_locally."""
+    if extended_compute_locally is not None:
+        ty, tx = _tiles(raster_settings)
+        if extended_compute_locally.numel() != ty * tx:
+            raise ValueError(f"extended_compute_locally must have {ty}x{tx} entries, got {tuple(extended_compute_locally.shape)}")
+        if compute_locally is not None and bool((compute_locally.reshape(-1).bool() & ~extended_compute_locally.reshape(-1).bool()).any()):
+            raise ValueError("extended_compute_locally must cover compute_locally")
     collector = None
     if isinstance(cuda_args, dict):
         collector = cuda_args.setdefault("stats_collector", {})

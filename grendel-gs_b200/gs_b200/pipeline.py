@@ -115,11 +115,15 @@ class Trainer:
 
     def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None,
                  fused_activations=True, border_exchange=False, batched_render=True, peer_exchange=None,
-                 peer_cap_rows=None, shard=None, load_balance=True, heuristic_decay=0.0):
+                 peer_cap_rows=None, shard=None, load_balance=True, heuristic_decay=0.0,
+                 distributed_dataset_storage=False):
         """scene: the WHOLE scene (sliced here into this rank's contiguous shard), or -- shard=(lo, hi, n_total) -- only
         this rank's Gaussians [lo, hi) of an n_total-Gaussian scene (synthetic.make_scene_shard).
         load_balance: feed the measured render times back into the strip division after every step
-        (finish_strategy_final, workload_division.py:944-998; only where the reference's gate enables it)."""
+        (finish_strategy_final, workload_division.py:944-998; only where the reference's gate enables it).
+        distributed_dataset_storage: only rank 0 holds the ground-truth images (gts_pinned may be None elsewhere); the
+        strips of a resident=False step are scattered from rank 0's GPU (loss_distribution.py:2395-2533, gt_scatter.py)
+        instead of being read from every rank's own host copy."""
         from . import exchange as _ex
         self._ex = _ex
         # splat / gradient rows travel by direct NVLink stores from the pack kernels (exchange.PeerBuffers) instead of
@@ -157,8 +161,10 @@ class Trainer:
         self.dcams = [DeviceCamera(c, device) for c in cams]
         self.H, self.W = self.dcams[0].image_height, self.dcams[0].image_width
         self.tile_y, self.tile_x = (self.H + 15) // 16, (self.W + 15) // 16
+        self.distributed_dataset_storage = bool(distributed_dataset_storage) and world > 1
         self.gts_host = gts_pinned                      # uint8 (3,H,W) pinned host tensors
-        self.gts_dev = [g.to(device) for g in gts_pinned]   # copies for the "inputs resident" leg
+        # copies for the "inputs resident" leg (not needed by ranks without pixels in distributed-storage mode)
+        self.gts_dev = [g.to(device) for g in gts_pinned] if gts_pinned is not None else None
         self.history = StrategyHistory([c.uid for c in self.dcams], self.tile_y, world)
         self._strip_cache = {}
         self._cams_packed = None   # (B,40) camera table of the batched preprocess (cameras are fixed per Trainer)
@@ -223,12 +229,22 @@ class Trainer:
                 self.balance_log.append((self.iteration, [list(st.division_pos) for st in new],
                                          [list(st.gpu_ids) for st in new]))
         strategies = self._strategy_cache[1]
+        self._tasks = [[(k, st.division_pos[st.gpu_ids.index(g)], st.division_pos[st.gpu_ids.index(g) + 1])
+                        for k, st in enumerate(strategies) if g in st.gpu_ids] for g in range(self.world)]
         settings = [c.settings(p.active_sh_degree) for c in self.dcams]
         # "Asynchronously load ground-truth image to GPU" (loss_distribution.py:2399): the strips this rank needs are
         # copied from pinned host memory on a side stream while preprocess / binning / blend run, and the loss waits
         # on the copy's event.
         gt_ready = {}
-        if not resident:
+        if not resident and self.distributed_dataset_storage:
+            from . import gt_scatter
+            strips, h2d = gt_scatter.scatter_gt_strips(self.gts_host if self.rank == 0 else self.W, self._tasks, self.H,
+                                                       self.device, self.rank, self.world, self.group)
+            self._h2d += h2d
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            gt_ready = {k: (t, ev) for k, t in strips.items()}
+        elif not resident:
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=self.device)
             for k, st in enumerate(strategies):

@@ -270,3 +270,39 @@ def test_layout_is_consistent_without_a_group():
     assert fits(holder, cnt)
     holder.cap_rows = total - 1
     assert not fits(holder, cnt)
+
+
+def _gt_scatter_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from gs_b200 import gt_scatter
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    H, W, B, tile_y = 100, 40, 3, 7
+    gts = [torch.from_numpy(np.random.default_rng(k).integers(0, 256, (3, H, W), dtype=np.uint8)) for k in range(B)]
+    hist = division.StrategyHistory(list(range(B)), tile_y, world)
+    _, tasks = division.start_strategy(list(range(B)), hist, world, rank)
+    got, h2d = gt_scatter.scatter_gt_strips(gts if rank == 0 else W, tasks, H, "cpu", rank, world)
+    ok = set(got) == {t[0] for t in tasks[rank]}
+    for cam, l, r in tasks[rank]:
+        y0, y1 = l * 16, min(r * 16, H)
+        ok = ok and torch.equal(got[cam], gts[cam][:, y0:y1, :])
+    q.put((rank, bool(ok), h2d))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gt_strips_scattered_from_rank0_match_the_local_slices(world):
+    """loss_distribution.py:2395-2533 with --distributed_dataset_storage: only rank 0 holds pixels; every rank ends up
+    with exactly the uint8 rows of its strips (3 cameras over 2 / 3 ranks: strips that start and end mid-image)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + world
+    procs = [ctx.Process(target=_gt_scatter_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] > 0 and all(h == 0 for _, _, h in res[1:])      # only rank 0 copied from the host
