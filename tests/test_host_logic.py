@@ -306,3 +306,64 @@ def test_gt_strips_scattered_from_rank0_match_the_local_slices(world):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert res[0][2] > 0 and all(h == 0 for _, _, h in res[1:])      # only rank 0 copied from the host
+
+
+def _redistribute_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from gs_b200 import redistribute as rd
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    P = 50 + 37 * rank                                   # uneven shards
+    g = torch.Generator().manual_seed(100 + rank)
+    shapes = {"xyz": (3,), "f_dc": (1, 3), "f_rest": (15, 3), "opacity": (1,), "scaling": (3,), "rotation": (4,)}
+    params = {k: torch.nn.Parameter(torch.randn((P,) + s, generator=g)) for k, s in shapes.items()}
+    opt = torch.optim.Adam([{"params": [params[k]], "lr": 1e-3, "name": k} for k in rd.NAMES], lr=0.0, eps=1e-15)
+    for k in rd.NAMES:
+        params[k].grad = torch.randn(params[k].shape, generator=g)
+    opt.step()
+    before = {k: (params[k].detach().clone(), opt.state[params[k]]["exp_avg"].clone(), opt.state[params[k]]["exp_avg_sq"].clone())
+              for k in rd.NAMES}
+    dest = torch.randint(0, world, (P,), generator=g)
+    need, counts = rd.need_redistribute(P, threshold=1.2)
+    res = rd.redistribute(opt, dest)
+    # what the reference builds, tensor by tensor: cat over sources i of state_i[destination_i == me]  (:1073-1098)
+    gathered = {}
+    for k in rd.NAMES:
+        for q_, t in enumerate(before[k]):
+            mine = [t[dest == j].contiguous() for j in range(world)]
+            outs = [None] * world
+            dist.all_gather_object(outs, mine)
+            gathered[(k, q_)] = torch.cat([outs[i][rank] for i in range(world)], dim=0)
+    ok = True
+    for k in rd.NAMES:
+        p_new = opt.param_groups[rd.NAMES.index(k)]["params"][0]
+        st = opt.state[p_new]
+        ok = ok and p_new is res[k] and p_new.requires_grad and torch.equal(p_new.detach(), gathered[(k, 0)])
+        ok = ok and torch.equal(st["exp_avg"], gathered[(k, 1)]) and torch.equal(st["exp_avg_sq"], gathered[(k, 2)])
+        ok = ok and float(st["step"]) == 1.0
+    n_new = res["xyz"].shape[0]
+    ok = ok and n_new == sum(row[rank] for row in res["counts"]) and res["send_to_gpui_cnt"].shape == (n_new, world)
+    for k in rd.NAMES:                                   # the optimizer keeps working on the moved tensors
+        res[k].grad = torch.ones_like(res[k])
+    opt.step()
+    q.put((rank, bool(ok), bool(need), counts, n_new))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_redistribution_in_one_collective_matches_the_reference_tensor_by_tensor(world):
+    """scene/gaussian_model.py:1073-1098 + :1262-1329: the fused-row all-to-all reproduces, row for row, the eighteen
+    per-tensor exchanges (parameters and Adam moments stay attached to their Gaussian; counts add up)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world
+    procs = [ctx.Process(target=_redistribute_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _, _ in res), res
+    assert all(need for _, _, need, _, _ in res)                       # 50 * 1.2 < 87: uneven enough
+    assert sum(n for *_, n in res) == sum(50 + 37 * r for r in range(world))
