@@ -293,6 +293,10 @@ GS_D float p2_hi(p2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "
 GS_D p2 p2_fma(p2 a, p2 b, p2 c) { p2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 GS_D p2 p2_mul(p2 a, p2 b) { p2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 GS_D p2 p2_add(p2 a, p2 b) { p2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// in-place forms for loop-carried accumulators: the tied operand keeps the value in ONE register pair across iterations
+// (separate result registers made ptxas copy every packed state variable back at the end of each iteration)
+GS_D void p2_fma_acc(p2 &c, p2 a, p2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }
+GS_D void p2_mul_acc(p2 &t, p2 f) { asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(t) : "l"(f)); }
 
 template <bool STATS, bool CKPT>
 __global__ void __launch_bounds__(F2_THREADS, F2_MIN_CTAS)
@@ -384,7 +388,9 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
                 const p2 pw = p2_fma(dx, p2_fma(p2_bc(a.z), dx, p2_bc(t)), p2_bc(u));
                 const float pw0 = p2_lo(pw), pw1 = p2_hi(pw);
                 const bool ok0 = has && pw0 >= b.z, ok1 = has && pw1 >= b.z;  // false for NaN
-                if (!__any_sync(FULL, ok0 || ok1)) continue;
+#ifndef F2_NO_EARLY_OUT
+                if (!__any_sync(FULL, ok0 || ok1)) continue;   // 9 % of the iterations on c2
+#endif
                 const p2 e = p2_mul(pw, p2_bc(1.4426950408889634f));
                 float G0, G1;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G0) : "f"(p2_lo(e)));
@@ -403,8 +409,8 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
                 const p2 ae = p2_make(bl0 ? al0 : 0.f, bl1 ? al1 : 0.f);
                 const p2 w = p2_mul(ae, T);
                 const float2 gb = *reinterpret_cast<const float2 *>(&sr->c);
-                C0 = p2_fma(p2_bc(b.w), w, C0); C1 = p2_fma(p2_bc(gb.x), w, C1); C2 = p2_fma(p2_bc(gb.y), w, C2);
-                T = p2_mul(T, p2_fma(ae, mone2, one2));
+                p2_fma_acc(C0, p2_bc(b.w), w); p2_fma_acc(C1, p2_bc(gb.x), w); p2_fma_acc(C2, p2_bc(gb.y), w);
+                p2_mul_acc(T, p2_fma(ae, mone2, one2));
                 last0 = bl0 ? (uint32_t)(base + j + 1) : last0; last1 = bl1 ? (uint32_t)(base + j + 1) : last1;
                 if (STATS) blended += (bl0 ? 1u : 0u) + (bl1 ? 1u : 0u);
             }

@@ -104,3 +104,23 @@ def densify_and_prune(optimizer, xyz_gradient_accum, denom, max_grad, min_opacit
         result["send_to_gpui_cnt"] = outs["send_to_gpui_cnt"]
     result["counts"] = (kept, clones, child1, S, new_P)
     return result
+
+
+def append_gaussians(optimizer, new_tensors):
+    """cat_tensors_to_optimizer (/root/reference/scene/gaussian_model.py:837-881): rows appended to every parameter, their
+    Adam moments start at zero, "step" is kept.  new_tensors: {group name: (n, ...) tensor}.  -> {name: new Parameter}."""
+    groups = {g["name"]: g for g in optimizer.param_groups}
+    out = {}
+    for k in NAMES:
+        g = groups[k]
+        old, ext = g["params"][0], new_tensors[k].to(device=g["params"][0].device, dtype=g["params"][0].dtype)
+        new = nn.Parameter(torch.cat((old.detach(), ext), dim=0).contiguous().requires_grad_(True))
+        st = optimizer.state.pop(old, None)
+        if st is not None:
+            if "exp_avg" in st:
+                st["exp_avg"] = torch.cat((st["exp_avg"], torch.zeros_like(ext)), dim=0)
+                st["exp_avg_sq"] = torch.cat((st["exp_avg_sq"], torch.zeros_like(ext)), dim=0)
+            optimizer.state[new] = st
+        g["params"][0] = new
+        out[k] = new
+    return out

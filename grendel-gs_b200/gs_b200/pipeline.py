@@ -433,6 +433,21 @@ class Trainer:
         times = allt.reshape(self.world, B).cpu().tolist()       # gpu_camera_running_time[gpu][camera]
         finish_strategy(self.history, strategies, times, self.iteration, self.world, self.H, self.W, self.heuristic_decay)
 
+    GROUP_OF = {"xyz": "_xyz", "f_dc": "_features_dc", "f_rest": "_features_rest", "opacity": "_opacity",
+                "scaling": "_scaling", "rotation": "_rotation"}
+
+    def optimizer_groups(self, lrs=None):
+        """The reference's six single-tensor groups over this trainer's parameters (scene/gaussian_model.py:257-292)."""
+        lrs = lrs or {"xyz": 0.00016, "f_dc": 0.0025, "f_rest": 0.0025 / 20, "opacity": 0.05, "scaling": 0.005,
+                      "rotation": 0.001}            # arguments/__init__.py:110-119
+        return [{"params": [getattr(self.params, attr)], "lr": lrs[name], "name": name} for name, attr in self.GROUP_OF.items()]
+
+    def adopt_parameters(self, new):
+        """After densification / redistribution replaced the optimizer's tensors: new = {group name: nn.Parameter}."""
+        for name, attr in self.GROUP_OF.items():
+            setattr(self.params, attr, new[name])
+        self.n_local = int(new["xyz"].shape[0])
+
     def last_info(self):
         """Realised sizes of the last step on this rank: V visible, V' splats rendered, R instances."""
         V = int((self._radii_local > 0).sum())
