@@ -56,9 +56,17 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
     // 64-bit instance total beside the 32-bit scan: a batch whose total reaches 2^32 would wrap the scan and pass the
     // R < 2^31 check with corrupted offsets (one atomic per warp)
     const uint32_t my_n = valid ? count_local_tiles(i, W, H, means2D, radii, compute_locally, views) : 0u;
-    {
+    {   // one 64-bit atomic per CTA (per-warp atomics on one address cost 20 us at 2 M splats)
+        __shared__ uint32_t s_sum[BIN_THREADS / 32];
         const uint32_t wsum = __reduce_add_sync(0xffffffffu, my_n);   // <= 32 * T: no overflow
-        if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(total64, (unsigned long long)wsum);
+        if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = wsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0ull;
+#pragma unroll
+            for (int w = 0; w < BIN_THREADS / 32; w++) t += s_sum[w];
+            if (t) atomicAdd(total64, t);
+        }
     }
     if (!valid) return;
     const uint32_t n = my_n;

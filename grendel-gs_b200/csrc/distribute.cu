@@ -771,6 +771,7 @@ GS_D int xr_local_rank(uint32_t h, int j, int warp, int lane, int32_t (*s_wcnt)[
 __global__ void __launch_bounds__(DT_THREADS)
 k_xr_pack(XrGeom g, XIn in, const int32_t *__restrict__ blkbase, XrPeers peers) {
     __shared__ int32_t s_wcnt[DT_THREADS / 32][XW];
+    __shared__ float s_rgb[DT_THREADS / 32][96];
     const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool valid = i < g.P;
@@ -796,19 +797,31 @@ k_xr_pack(XrGeom g, XIn in, const int32_t *__restrict__ blkbase, XrPeers peers) 
     while (any) {
         const int j = __ffs(any) - 1;
         any &= any - 1u;
-        const int lr = xr_local_rank(h, j, warp, lane, s_wcnt);
-        if (!((h >> j) & 1u)) continue;
+        // the warp's hits for destination j are consecutive rows: every field is one contiguous span, written with
+        // consecutive lanes on consecutive addresses (rgb, 12 B per row, goes through a shared-memory transpose: strided
+        // 4-byte stores are partial sectors on NVLink).  Visibility to the peer: kernel completion + the stream-ordered
+        // barrier the caller enqueues -- no per-thread system fence.
+        const uint32_t bal = __ballot_sync(0xffffffffu, (h >> j) & 1u);
+        const int wr = __popc(bal & ((1u << lane) - 1u)), wn = __popc(bal);
+        int lr = wr;
+        for (int w = 0; w < warp; w++) lr += s_wcnt[w][j];
+        const bool hit = (h >> j) & 1u;
         const size_t col = (size_t)j * g.B + k;
         const long long row = (long long)peers.row0[col] + (blkbase[col * gridDim.x + blockIdx.x] - blkbase[col * gridDim.x]) + lr;
         float *b = reinterpret_cast<float *>(peers.base[j]);
-        *reinterpret_cast<float2 *>(b + 2 * row) = m;
-        float *q = b + 2 * cap + 3 * row;
-        q[0] = r0; q[1] = r1; q[2] = r2;
-        *reinterpret_cast<float4 *>(b + 5 * cap + 4 * row) = co;
-        reinterpret_cast<int32_t *>(b + 9 * cap)[row] = rad;
-        (b + 10 * cap)[row] = dep;
+        if (hit) {
+            *reinterpret_cast<float2 *>(b + 2 * row) = m;
+            *reinterpret_cast<float4 *>(b + 5 * cap + 4 * row) = co;
+            reinterpret_cast<int32_t *>(b + 9 * cap)[row] = rad;
+            (b + 10 * cap)[row] = dep;
+            s_rgb[warp][3 * wr] = r0; s_rgb[warp][3 * wr + 1] = r1; s_rgb[warp][3 * wr + 2] = r2;
+        }
+        const long long row_w = __shfl_sync(0xffffffffu, row - wr, __ffs(bal) - 1);   // first row of the warp's span
+        __syncwarp();
+        float *q = b + 2 * cap + 3 * row_w;
+        for (int t = lane; t < 3 * wn; t += 32) q[t] = s_rgb[warp][t];
+        __syncwarp();
     }
-    __threadfence_system();
 }
 
 __global__ void __launch_bounds__(DT_THREADS)
@@ -837,10 +850,10 @@ k_xr_pull_grad(XrGeom g, const int32_t *__restrict__ blkbase, XrPeers peers, XOu
         const long long row = (long long)peers.row0[col] + (blkbase[col * gridDim.x + blockIdx.x] - blkbase[col * gridDim.x]) + lr;
         const float *b = reinterpret_cast<const float *>(peers.base[j]);
         const float2 a = *reinterpret_cast<const float2 *>(b + 2 * row);
-        const float *q = b + 2 * cap + 3 * row;
-        const float4 c = *reinterpret_cast<const float4 *>(b + 5 * cap + 4 * row);
+        const float4 q = *reinterpret_cast<const float4 *>(b + 2 * cap + 4 * row);   // d rgb, padded to 16 B per row
+        const float4 c = *reinterpret_cast<const float4 *>(b + 6 * cap + 4 * row);
         dm.x += a.x; dm.y += a.y;
-        d0 += q[0]; d1 += q[1]; d2 += q[2];
+        d0 += q.x; d1 += q.y; d2 += q.z;
         dco.x += c.x; dco.y += c.y; dco.z += c.z; dco.w += c.w;
     }
     if (valid) {
@@ -933,7 +946,7 @@ extern "C" int gs_xr_pack(int B, int P, int W, int image_height, int image_width
     return GS_OK;
 }
 
-// peer_grad_ptrs_host[j]: rank j's gradient region (9 * cap floats: d means2D | d rgb | d conic_opacity); the outputs
+// peer_grad_ptrs_host[j]: rank j's gradient region (10 * cap floats: d means2D (2) | d rgb padded to 4 | d conic_opacity (4)); the outputs
 // are the (B,P,.) gradients of this rank's projected splats: the sum over the destinations each splat was sent to.
 extern "C" int gs_xr_pull_grad(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
                                const void *const *radii_ptrs_host, const int32_t *row_lo_host, const int32_t *row_hi_host,

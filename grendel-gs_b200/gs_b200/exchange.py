@@ -154,7 +154,9 @@ class PeerBuffers:
         # or all ranks raise -- never a rank stuck alone in a collective
         handles, err = [0] * 128, None
         try:
-            for q, nbytes in enumerate((self.cap_rows * ROW * 4, self.cap_rows * GROW * 4)):
+            # gradient buffer: 10 floats per row (the direct-placement layout pads d rgb to 16 bytes; the row-staged path
+            # uses 9 of them)
+            for q, nbytes in enumerate((self.cap_rows * ROW * 4, self.cap_rows * (GROW + 1) * 4)):
                 ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
                 _lib.call("gs_peer_alloc", nbytes, C.byref(ptr), handle)
                 self._owned.append(ptr.value)
@@ -203,14 +205,14 @@ class PeerBuffers:
     def views(self):
         """This rank's own buffers as torch tensors in the structure-of-arrays layout of the direct-placement exchange
         (csrc/distribute.cu "xr"): ((means2D (cap,2), rgb (cap,3), conic_opacity (cap,4), radii (cap) int32, depths (cap)),
-        (d means2D, d rgb, d conic_opacity)) -- zero-copy views of the peer-visible memory."""
+        (d means2D, d rgb [a (cap,3) view of 16-byte rows], d conic_opacity)) -- zero-copy views of the peer-visible memory."""
         if self._views is None:
             cap, dev = self.cap_rows, self.device
             r, g = self.recv[self.me], self.grad[self.me]
             f = lambda base, off, shape: _wrap(base + 4 * off * cap, shape, "<f4", dev)
             self._views = ((f(r, 0, (cap, 2)), f(r, 2, (cap, 3)), f(r, 5, (cap, 4)),
                             _wrap(r + 4 * 9 * cap, (cap,), "<i4", dev), f(r, 10, (cap,))),
-                           (f(g, 0, (cap, 2)), f(g, 2, (cap, 3)), f(g, 5, (cap, 4))))
+                           (f(g, 0, (cap, 2)), f(g, 2, (cap, 4))[:, :3], f(g, 6, (cap, 4))))
         return self._views
 
     def fits_direct(self, cnt):
@@ -370,21 +372,14 @@ class _ExchangeSplats(torch.autograd.Function):
 
 
 class _ExchangeSplatsDirect(torch.autograd.Function):
-    """Same contract as _ExchangeSplats over the direct-placement kernels: the pack kernel stores every field into its final
-    row of the destination's arrays (the outputs ARE views of this rank's peer-visible receive region: no unpack), and the
-    backward pulls the gradient rows from the destinations' gradient regions."""
+    """Same contract as _ExchangeSplats over the direct-placement kernels: the pack kernel has stored every field into its
+    final row of the destination's arrays (launched by exchange_cat right after the counts arrived, so that the GPU idles as
+    briefly as possible behind the step's host sync); the outputs ARE views of this rank's peer-visible receive region (no
+    unpack), and the backward pulls the gradient rows from the destinations' gradient regions."""
 
     @staticmethod
     def forward(ctx, state, m2, rgb, co):
-        B, P, W, peer = state["B"], state["P"], state["W"], state["peer"]
-        m2, rgb, co = m2.contiguous(), rgb.contiguous(), co.contiguous()
-        s = ops._stream()
-        _lib.call("gs_xr_pack", B, P, W, state["H"], state["Wimg"], _slab_ptrs(state["m2d"], B), _slab_ptrs(rgb, B),
-                  _slab_ptrs(co, B), _slab_ptrs(state["radii"], B), _slab_ptrs(state["depths"], B), state["lo"], state["hi"],
-                  state["blkbase"].data_ptr(), (C.c_void_p * W)(*peer.recv), state["row0"], C.c_longlong(peer.cap_rows), s)
-        _t("x3 pack")
-        peer.barrier()
-        _t("x4 all_to_all")
+        B, peer = state["B"], state["peer"]
         N = state["view_start"][B]
         (v_m2, v_rgb, v_co, v_rad, v_dep), _ = peer.views()
         om2, orgb, oco, orad, odep = v_m2[:N], v_rgb[:N], v_co[:N], v_rad[:N], v_dep[:N]
@@ -481,12 +476,26 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
         _lib.call("gs_xr_count", B, P, world, H, Wimg, _slab_ptrs(m2d, B), _slab_ptrs(radii, B), lo_c, hi_c,
                   blkcnt.data_ptr(), blkbase.data_ptr(), counts.data_ptr(), temp.data_ptr(), tb, ops._stream())
         _t("x1 route")
+        # everything the pack launch needs is prepared BEFORE the host waits for the counts: the GPU is idle from the
+        # all-gather until the pack kernel starts
+        rgb_c, co_c = rgb.detach().contiguous(), conic_opacity.detach().contiguous()
+        pack_args = (B, P, world, H, Wimg, _slab_ptrs(m2d, B), _slab_ptrs(rgb_c, B), _slab_ptrs(co_c, B),
+                     _slab_ptrs(radii, B), _slab_ptrs(depths, B), lo_c, hi_c, blkbase.data_ptr(),
+                     (C.c_void_p * world)(*peer.recv))
+        cap, stream = C.c_longlong(peer.cap_rows), ops._stream()
         cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]
         _t("x2 gather counts")
-        if peer.fits_direct(cnt):   # decided from the all-gathered counts: identical on all ranks
-            row0, view_start = direct_rows(cnt, me)
+        c64 = np.asarray(cnt, dtype=np.int64)
+        if int(c64.sum(axis=(0, 1)).max()) <= peer.cap_rows:
+            row0, view_start = direct_rows(c64, me)       # decided from the all-gathered counts: identical on all ranks
+            row0_c = _i32(row0)
+            _lib.call("gs_xr_pack", *pack_args, row0_c, cap, stream)
+            _t("x3 pack")
+            peer.barrier()
+            _t("x4 all_to_all")
             state = dict(group=group, radii=radii, depths=depths, m2d=m2d, blkbase=blkbase, B=B, P=P, W=world, H=H,
-                         Wimg=Wimg, lo=lo_c, hi=hi_c, row0=_i32(row0), view_start=view_start, peer=peer, cnt=cnt, me=me)
+                         Wimg=Wimg, lo=lo_c, hi=hi_c, row0=row0_c, view_start=view_start, peer=peer, cnt=cnt, me=me,
+                         keep=(rgb_c, co_c))
             res = _ExchangeSplatsDirect.apply(state, means2D, rgb, conic_opacity)
             return res, view_start, cnt
         # does not fit the buffers this step: the row-staged path below (all_to_all_single) handles any size

@@ -363,7 +363,8 @@ GS_API int gs_xchg_pack_grad_p2p(int nseg, const int32_t *seg_recv_start_host, c
  * receive region (means2D | rgb | conic_opacity | radii | depths, cap_rows rows each; gs_peer_alloc'ed, 11*cap floats),
  * i.e. straight into the tensors that rank's render reads -- no send rows, no unpack (replaces :590-607 and :631-658).
  * gs_xr_pull_grad: the mirrored backward; the owner of a splat loads its gradient rows from the gradient regions
- * (d means2D | d rgb | d conic_opacity, 9*cap floats) of the ranks it sent the splat to and sums them.
+ * (d means2D (2) | d rgb padded to 4 floats per row | d conic_opacity (4): 10*cap floats) of the ranks it sent the
+ * splat to and sums them.
  * row_lo/row_hi: (B*W) HOST ints as in gs_xchg_route; dst_row0_host[j*B+k]: first row of the calling rank's block inside
  * camera k of rank j's arrays (from the all-gathered counts).  The caller orders pack -> consumers and the gradient
  * writers -> pull across ranks (a stream-ordered barrier). */

@@ -189,6 +189,30 @@ def test_backward_kernels_agree(o32, n, W, H, rad, bg):
         assert (a[~np.isin(np.arange(n), rf["ids"])] == 0).all()
 
 
+@pytest.mark.parametrize("n,W,H,rad,bg", [(20000, 320, 200, 7.0, (0.0, 0.0, 0.0)), (3000, 97, 61, 16.0, (0.3, 0.1, 0.7)),
+                                          (60000, 100, 70, 12.0, (0.1, 0.2, 0.3))])
+def test_forward_kernels_agree(o32, n, W, H, rad, bg):
+    """The packed two-pixels-per-lane forward (k_blend_fwd2, default) and round 1's half-warp forward (k_blend_fwd,
+    gs_debug_set(GS_DEBUG_FWD_HALFWARP)) run the same per-pixel operation sequence: image, final_T, n_contrib, the
+    statistics AND the checkpoints the segment backward reads are bit-identical (ragged image edges included)."""
+    from gs_b200 import _lib
+    ref, rf, f, cl = _render_case(o32, n, W, H, rad, bg)
+    g = gu.to_dev(np.random.default_rng(3).normal(size=(3, H, W)).astype(np.float32))
+    b_new = gu.render_backward(f, g)
+    old = _lib.debug_set(_lib.DEBUG_FWD_HALFWARP)
+    try:
+        f1 = gu.render_forward(H, W, gu.to_dev(ref["means2D"]), gu.to_dev(ref["conic_opacity"]), gu.to_dev(ref["rgb"]),
+                               gu.to_dev(ref["depths"]), gu.to_dev(ref["radii"]), gu.to_dev(cl), bg)
+    finally:
+        _lib.debug_set(old)
+    for k in ("image", "final_T", "n_contrib", "stats"):
+        assert torch.equal(f[k], f1[k]), k
+    b_old = gu.render_backward(f1, g)          # the segment backward on the OTHER forward's checkpoints
+    for k in ("means2D", "conic_opacity", "rgb"):
+        a, b = b_new[k].double(), b_old[k].double()
+        assert float(((a - b).abs() > 1e-5 * b.abs() + 1e-5 * b.abs().mean()).double().mean()) <= 1e-4, k
+
+
 def test_whole_step_parity_config_c1(o32, o64):
     """BASELINE.json configs[0]: 50k Gaussians, 400x400, forward + loss + backward, through the public operator.
     Whole-step gradients compound the forward's rounding through the SSIM derivative (divisions by small variances) and the
