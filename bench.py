@@ -338,8 +338,14 @@ def run_ours(args):
         phase_ms = {k: round(float(v), 4) for k, v in zip(keys, tt.tolist())}
     exchange_kind = None
     if world > 1:
-        exchange_kind = ("NVLink peer-memory stores fused into the pack kernels (gs_xchg_pack_p2p)"
-                         if trainer._peer is not None else "NCCL all_to_all_single")
+        from gs_b200 import exchange as _ex
+        if trainer._peer is None:
+            exchange_kind = "NCCL all_to_all_single"
+        elif _ex.MODE == "direct":
+            exchange_kind = ("direct placement over NVLink peer memory: k_xr_pack stores every field into its final row of the "
+                             "destination's SoA receive region, the backward pulls gradient rows (gs_xr_*)")
+        else:
+            exchange_kind = "NVLink peer-memory stores fused into the row pack kernels (gs_xchg_pack_p2p)"
     balance_log = list(trainer.balance_log)
 
     # ---- extras at N > 1, OUTSIDE the timed regions: (a) the strong-scaling direction the headline does not exercise

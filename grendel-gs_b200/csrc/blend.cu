@@ -67,17 +67,69 @@ GS_D Where where_am_i(int tile, int gx) {
     return p;
 }
 
-// bit (by*4+bx) set <=> the splat's bounding box (centre m, half extents e) overlaps 4x4 block (bx,by)
-GS_D uint32_t block_mask16(float mx, float my, float ex, float ey, float X0, float Y0) {
-    if (ex < 0.f) return 0u;
-    const float xl = mx - ex - X0, xh = mx + ex - X0, yl = my - ey - Y0, yh = my + ey - Y0;
-    uint32_t xm = 0u, m = 0u;
+// Row-band extents of the splat's {power >= thr} ellipse.  The bounding box alone keeps every block of the box's
+// corners, which a diagonal or elongated ellipse never reaches: on c2 a third of the (4x4 block, splat) candidates of the
+// forward and a quarter of the backward's (8x4 block, splat) passes ended in the "no pixel passes the exponent test"
+// exit.  For the four bands of four pixel rows of the tile, [xl, xh] is the exact x-range (tile coordinates) that
+//   alpha' u^2 + beta' u v + gamma' v^2 <= tau     (u, v relative to the centre; alpha' = -a', beta' = -b', gamma' = -c', tau = -thr)
+// covers over v in the band: the right boundary r(v) = kappa v + sqrt(tau/alpha') sqrt(1 - v^2/ey0^2), kappa = -beta'/(2 alpha'), is
+// concave with its maximum at v_r = -beta' ex0 / (2 gamma') (the ellipse's rightmost point), so its maximum over the band is
+// r(clamp(v_r, band)); the left boundary is the point mirror image.  ex0 / ey0 are the box's half extents as k_count_tiles
+// computed them (compensated determinant), so needle-shaped conics do not cancel here either.  Widened by 2 % + 0.05 px
+// in both directions (thr itself carries the 0.02 exponent margin): conservative, per-pixel results are unchanged
+// (test_needle_splats_survive_block_culling, culled == unculled bit for bit).  Degenerate conics (ex = 3e38) and
+// GS_DEBUG_NO_BLOCK_CULL keep every band of the box.
+#define GS_BAND_ABS_MARGIN 0.05f
+// approximate MUFU forms (relative error ~1e-7, three orders of magnitude inside the margins; the IEEE forms cost a
+// fix-up branch each, eight times per staged splat)
+GS_D float gs_rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+GS_D float gs_sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+GS_D void ellipse_bands(const float4 a, const float4 b, const float ex, const float ey, const float X0, const float Y0,
+                        float (&xl)[4], float (&xh)[4]) {
+    if (ex < 0.f) {
 #pragma unroll
-    for (int b = 0; b < 4; b++)
-        if (xh >= 4.f * b && xl <= 4.f * b + 3.f) xm |= 1u << b;
+        for (int q = 0; q < 4; q++) { xl[q] = 1e30f; xh[q] = -1e30f; }
+        return;
+    }
+    const bool exact = ex < 1e30f;
+    const float ex0 = (ex - 0.5f) * (1.f / 1.02f), ey0 = (ey - 0.5f) * (1.f / 1.02f);
+    const float mgx = 0.02f * ex0 + GS_BAND_ABS_MARGIN, mgy = 0.02f * ey0 + GS_BAND_ABS_MARGIN;
+    const float inv_a = gs_rcp_approx(-a.z);         // 1 / alpha'
+    const float kappa = 0.5f * a.w * inv_a;       // -beta' / (2 alpha')   (beta' = -a.w, alpha' = -a.z)
+    const float hw2 = -b.z * inv_a;               // tau / alpha'
+    const float v_r = -0.5f * a.w * ex0 * gs_rcp_approx(b.x);  // -beta' ex0 / (2 gamma') = -(-a.w) ex0 / (2 (-b.x))
+    const float inv_ey0 = gs_rcp_approx(ey0);
+    const float cx = a.x - X0;
 #pragma unroll
-    for (int b = 0; b < 4; b++)
-        if (yh >= 4.f * b && yl <= 4.f * b + 3.f) m |= xm << (4 * b);
+    for (int q = 0; q < 4; q++) {
+        const float v0 = (Y0 + 4.f * q) - a.y, v1 = v0 + 3.f;
+        float l = 1e30f, h = -1e30f;
+        if (v1 >= -ey && v0 <= ey) {
+            l = -1e30f; h = 1e30f;
+            if (exact) {
+                const float lo = v0 - mgy, hi = v1 + mgy;
+                const float vh = fminf(fmaxf(v_r, lo), hi), vl = fminf(fmaxf(-v_r, lo), hi);
+                const float qh = vh * inv_ey0, ql = vl * inv_ey0;
+                const float sh = fmaxf(0.f, 1.f - qh * qh), sl = fmaxf(0.f, 1.f - ql * ql);
+                h = cx + (kappa * vh + gs_sqrt_approx(hw2 * sh) + mgx);
+                l = cx + (kappa * vl - gs_sqrt_approx(hw2 * sl) - mgx);
+            }
+        }
+        xl[q] = l; xh[q] = h;
+    }
+}
+
+// bit (by*4+bx) set <=> the splat's ellipse can reach 4x4 block (bx,by)
+GS_D uint32_t block_mask16(const float4 a, const float4 b, float ex, float ey, float X0, float Y0) {
+    float xl[4], xh[4];
+    ellipse_bands(a, b, ex, ey, X0, Y0, xl, xh);
+    uint32_t m = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+        for (int bx = 0; bx < 4; bx++)
+            if (xh[q] >= 4.f * bx && xl[q] <= 4.f * bx + 3.f) m |= 1u << (4 * q + bx);
+    }
     return m;
 }
 
@@ -97,11 +149,13 @@ struct SegWs {
     uint32_t *tile_last;  // [T] deepest contributing entry of the tile (max n_contrib over its pixels)
     uint2 *units;         // [R / SEG_K + T] (tile, segment)
     float4 *ckpt;         // [(R / SEG_K + T + 1) * SEG_SLOT]
+    uint16_t *cull;       // [R] the forward's 4x4-block mask of every entry it staged (the backward never walks further)
 };
 static size_t seg_align(size_t v) { return (v + 255) / 256 * 256; }
 static size_t seg_bytes(int64_t R, int64_t T) {
     const size_t slots = (size_t)(R / SEG_K + T + 1);
-    return 256 + seg_align((size_t)T * 4) + seg_align(slots * sizeof(uint2)) + slots * SEG_SLOT * sizeof(float4);
+    return 256 + seg_align((size_t)T * 4) + seg_align(slots * sizeof(uint2)) + slots * SEG_SLOT * sizeof(float4) +
+           seg_align((size_t)R * sizeof(uint16_t));
 }
 static SegWs seg_carve(void *ws, int64_t R, int64_t T) {
     const size_t slots = (size_t)(R / SEG_K + T + 1);
@@ -110,7 +164,8 @@ static SegWs seg_carve(void *ws, int64_t R, int64_t T) {
     w.n_units = (uint32_t *)p; p += 256;
     w.tile_last = (uint32_t *)p; p += seg_align((size_t)T * 4);
     w.units = (uint2 *)p; p += seg_align(slots * sizeof(uint2));
-    w.ckpt = (float4 *)p;
+    w.ckpt = (float4 *)p; p += slots * SEG_SLOT * sizeof(float4);
+    w.cull = (uint16_t *)p;
     return w;
 }
 extern "C" size_t gs_render_seg_bytes(int64_t R, int num_tiles) { return seg_bytes(R > 0 ? R : 0, num_tiles > 0 ? num_tiles : 0); }
@@ -170,7 +225,9 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
             s_rec[threadIdx.x].a = a; s_rec[threadIdx.x].b = b; s_rec[threadIdx.x].c = c;
-            s_cull[threadIdx.x] = (uint16_t)block_mask16(a.x, a.y, c.z, c.w, X0, Y0);
+            const uint16_t m16 = (uint16_t)block_mask16(a, b, c.z, c.w, X0, Y0);
+            s_cull[threadIdx.x] = m16;
+            if (CKPT) seg.cull[range.x + base + threadIdx.x] = m16;
         }
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {
@@ -350,7 +407,9 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
             s_rec[i].a = a; s_rec[i].b = b; s_rec[i].c = c;
-            s_cull[i] = (uint16_t)block_mask16(a.x, a.y, c.z, c.w, X0, Y0);
+            const uint16_t m16 = (uint16_t)block_mask16(a, b, c.z, c.w, X0, Y0);
+            s_cull[i] = m16;
+            if (CKPT) seg.cull[range.x + base + i] = m16;
         }
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {
@@ -488,15 +547,16 @@ GS_D void pixel_of_thread(int tile, int gx, int &px, int &py) {
     py = (tile / gx) * GS_BLOCK_Y + (w >> 1) * 4 + (lane >> 3);
 }
 
-// bit w set <=> the splat's bounding box (centre m, half extents e) overlaps warp w's 8x4 pixel block
-GS_D uint32_t block_mask(float mx, float my, float ex, float ey, float X0, float Y0) {
-    if (ex < 0.f) return 0u;
-    const float xl = mx - ex - X0, xh = mx + ex - X0, yl = my - ey - Y0, yh = my + ey - Y0;
-    const uint32_t xm = ((xh >= 0.f && xl <= 7.f) ? 1u : 0u) | ((xh >= 8.f && xl <= 15.f) ? 2u : 0u);
+// bit w set <=> the splat's ellipse can reach warp w's 8x4 pixel block (w = 2 * band + column half)
+GS_D uint32_t block_mask(const float4 a, const float4 b, float ex, float ey, float X0, float Y0) {
+    float xl[4], xh[4];
+    ellipse_bands(a, b, ex, ey, X0, Y0, xl, xh);
     uint32_t m = 0u;
 #pragma unroll
-    for (int wy = 0; wy < 4; wy++)
-        if (yh >= 4.f * wy && yl <= 4.f * wy + 3.f) m |= xm << (2 * wy);
+    for (int wy = 0; wy < 4; wy++) {
+        if (xh[wy] >= 0.f && xl[wy] <= 7.f) m |= 1u << (2 * wy);
+        if (xh[wy] >= 8.f && xl[wy] <= 15.f) m |= 2u << (2 * wy);
+    }
     return m;
 }
 
@@ -588,7 +648,7 @@ k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), cc = __ldg(r + 2);
             s_rec[threadIdx.x].a = a; s_rec[threadIdx.x].b = b; s_rec[threadIdx.x].c = cc;
-            s_cull[threadIdx.x] = (uint8_t)block_mask(a.x, a.y, cc.z, cc.w, X0, Y0);
+            s_cull[threadIdx.x] = (uint8_t)block_mask(a, b, cc.z, cc.w, X0, Y0);
         }
         uint32_t wmask = 0u;  // lane q holds bits [32q, 32q+32) of "this warp produced a partial for entry j"
         __syncthreads();
@@ -691,7 +751,7 @@ k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
 #endif
 // values needed only when a pass is staged (every 32 entries) or in the per-splat tail live in shared memory, not in
 // registers: the walk keeps 16 state + 9 sum + 12 record registers per lane and wants 8 CTAs per SM
-struct SegCold { const uint32_t *ids; int cnt, X0, Y0; uint32_t blive, blive_hi; };
+struct SegCold { const uint32_t *ids; const uint16_t *cull; int cnt; uint32_t blive, blive_hi; };
 
 __global__ void __launch_bounds__(SG_THREADS, SG_MIN_CTAS)
 k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, const float *__restrict__ bg,
@@ -765,7 +825,7 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
         s_role_all[warp][lane] = make_uint4((uint32_t)rp, (uint32_t)(rp >> 32), rstride, __float_as_uint(rscale));
         if (lane == 0) {
             SegCold c;
-            c.ids = ids + range.x + seg_base; c.cnt = cnt; c.X0 = X0; c.Y0 = Y0; c.blive = blive; c.blive_hi = blive_hi;
+            c.ids = ids + range.x + seg_base; c.cull = seg.cull + range.x + seg_base; c.cnt = cnt; c.blive = blive; c.blive_hi = blive_hi;
             s_cold_all[warp] = c;
         }
     }
@@ -784,14 +844,20 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
             const uint32_t g = cold.ids[i];
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-            uint32_t m = block_mask(a.x, a.y, c.z, c.w, (float)cold.X0, (float)cold.Y0);
+            // the forward's 4x4-block mask of this entry (ellipse_bands, computed once per (splat, tile)); an 8x4 block is
+            // two horizontally adjacent 4x4 blocks: OR the bit pairs, then pack the even bits
+            uint32_t m = cold.cull[i];
+            m = (m | (m >> 1)) & 0x5555u;
+            m = (m | (m >> 1)) & 0x3333u;
+            m = (m | (m >> 2)) & 0x0f0fu;
+            m = (m | (m >> 4)) & 0x00ffu;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const uint32_t bl = ((q < 4 ? cold.blive : cold.blive_hi) >> (8 * (q & 3))) & 0xffu;
                 if ((uint32_t)i >= bl) m &= ~(1u << q);
             }
             s_rec[lane].a = a; s_rec[lane].b = b;
-            s_rec[lane].c = make_float4(c.x, c.y, __frcp_rn(b.y), __uint_as_float(g));
+            s_rec[lane].c = make_float4(c.x, c.y, gs_rcp_approx(b.y), __uint_as_float(g));
             s_mask[lane] = m;
         }
         __syncwarp();
@@ -848,7 +914,9 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
             const uint4 ro = *s_role;
             const float val = (lane == 1 ? v[8] : v[0]) * __uint_as_float(ro.w);
             float *rptr = reinterpret_cast<float *>((unsigned long long)ro.x | ((unsigned long long)ro.y << 32));
-            if (rptr) atomicAdd(rptr + (size_t)__float_as_uint(s_rec[jl].c.w) * ro.z, val);
+            // red.global: the pointer was rebuilt from integers, so a plain atomicAdd compiles to a GENERIC atomic with
+            // an address-space check and a shared-memory CAS fallback behind it
+            if (rptr) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(rptr + (size_t)__float_as_uint(s_rec[jl].c.w) * ro.z), "f"(val) : "memory");
         }
     }
 }

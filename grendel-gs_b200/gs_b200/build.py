@@ -70,10 +70,12 @@ def build(force=False, verbose=False, defs=(), variant=None):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [cc, *ARCH, "-shared", "-o", lib_out, *objs, "-cudart", "static"]
+    tmp_out = lib_out + f".tmp{os.getpid()}"   # linked beside the target and renamed: a reader never sees half a library
+    cmd = [cc, *ARCH, "-shared", "-o", tmp_out, *objs, "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp_out, lib_out)
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         for k in sorted(logs):
             f.write(f"==== {k}\n{logs[k]}\n")
