@@ -17,14 +17,16 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include <atomic>
+#include <mutex>
 
 #define BIN_THREADS 256
-#define GS_THR_MARGIN 0.02f
 
 // Stages 21-24: per-splat number of LOCAL tiles its rectangle touches, its depth sort key, and the packed
 // 48-byte record the blend kernels gather:
 //   r0 = (mx, my, a', b')      a' = -A/2, b' = -B, c' = -C/2  so that  power = a'dx^2 + b'dx dy + c'dy^2
-//   r1 = (c', opacity, thr, red)     thr = ln(1/(255*opacity)) - margin: power < thr  =>  alpha < 1/255
+//   r1 = (c', opacity, thr, red)     thr = ln(1/(255*opacity)): power < thr  <=>  alpha < 1/255 -- THE per-pixel test of the
+//                                    blend kernels (no second test on the computed alpha: the exponent decides)
 //   r2 = (green, blue, ex, ey)       half extents of the bounding box of {power >= thr} (+0.5 px slack),
 //                                    used by the blend kernels to cull splats per 4x4 / 8x4 pixel block
 GS_D uint32_t count_local_tiles(int i, int W, int H, const float *__restrict__ means2D, const int32_t *__restrict__ radii,
@@ -77,7 +79,7 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     if (n > 0) {
         const float4 co = *reinterpret_cast<const float4 *>(conic_opacity + 4 * i);
-        const float thr = -logf(255.0f * fmaxf(co.w, 1e-30f)) - GS_THR_MARGIN;
+        const float thr = -logf(255.0f * fmaxf(co.w, 1e-30f));
         // {d : A dx^2 + 2B dx dy + C dy^2 <= -2 thr} has half extents sqrt(t C/det), sqrt(t A/det)
         // det = AC - B^2 cancels catastrophically for needle-like splats (relative error ~ulp * lambda_max/lambda_min),
         // which would shrink the box and drop real contributions: evaluate it with Kahan's FMA-compensated ab - cd,
@@ -174,15 +176,47 @@ static int make_views(int num_views, const int32_t *view_start, int T, GsViews &
     return GS_OK;
 }
 
-extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start, int image_height, int image_width,
-                                       const float *means2D, const float *conic_opacity, const float *rgb,
-                                       const float *depths, const int32_t *radii, const uint8_t *compute_locally,
-                                       uint32_t *order, uint32_t *offsets, float *rec, void *temp, size_t temp_bytes,
-                                       int64_t *R_host, void *stream_) {
+// The instance total travels to the host through a small ring of pinned 8-byte slots owned by the library, so that the
+// launch half of the count can return before the device has produced it (the caller prepares the next launch meanwhile).
+#define GS_COUNT_SLOTS 64
+static unsigned long long *g_count_slots = nullptr;
+static cudaEvent_t g_count_events[GS_COUNT_SLOTS];
+static std::atomic<unsigned> g_count_next{0};
+static std::mutex g_count_mutex;
+
+static unsigned long long *count_slot() {
+    {
+        std::lock_guard<std::mutex> lock(g_count_mutex);
+        if (!g_count_slots) {
+            if (cudaHostAlloc((void **)&g_count_slots, GS_COUNT_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) {
+                g_count_slots = nullptr;
+                return nullptr;
+            }
+            for (int i = 0; i < GS_COUNT_SLOTS; i++)
+                if (cudaEventCreateWithFlags(&g_count_events[i], cudaEventDisableTiming) != cudaSuccess) {
+                    cudaFreeHost(g_count_slots);
+                    g_count_slots = nullptr;
+                    return nullptr;
+                }
+        }
+    }
+    return g_count_slots + (g_count_next.fetch_add(1) % GS_COUNT_SLOTS);
+}
+
+extern "C" int gs_render_count_launch(int num_views, const int32_t *view_start, int P1, int image_height, int image_width,
+                                      const float *means2D, const float *conic_opacity, const float *rgb,
+                                      const float *depths, const int32_t *radii, const uint8_t *compute_locally,
+                                      uint32_t *order, uint32_t *offsets, float *rec, void *temp, size_t temp_bytes,
+                                      void **ticket, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GS_REQUIRE(image_height > 0 && image_width > 0, "sizes");
-    GS_REQUIRE(R_host != nullptr, "R_host");
-    *R_host = 0;
+    GS_REQUIRE(ticket != nullptr, "ticket");
+    *ticket = nullptr;
+    const int32_t one_view[2] = {0, P1};
+    if (view_start == nullptr) {   // the single-camera form: one view of P1 splats
+        GS_REQUIRE(num_views == 1 && P1 >= 0, "view_start may only be NULL for one view");
+        view_start = one_view;
+    }
     GsViews views;
     {
         const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;
@@ -190,7 +224,14 @@ extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start,
         if (rc != GS_OK) return rc;
     }
     const int P = views.start[num_views];
-    if (P == 0) return GS_OK;
+    unsigned long long *slot = count_slot();
+    GS_REQUIRE(slot != nullptr, "pinned host slot for the instance count");
+    *slot = 0ull;
+    *ticket = slot;
+    if (P == 0) {
+        GS_CUDA_TRY(cudaEventRecord(g_count_events[slot - g_count_slots], stream));
+        return GS_OK;
+    }
     GS_REQUIRE(means2D && conic_opacity && rgb && depths && radii && compute_locally && order && offsets && rec && temp,
                "null pointer");
     GS_REQUIRE(((uintptr_t)rec & 15) == 0 && ((uintptr_t)conic_opacity & 15) == 0 && ((uintptr_t)means2D & 7) == 0,
@@ -215,6 +256,11 @@ extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start,
                                                         (g_gs_debug_flags & GS_DEBUG_NO_BLOCK_CULL) ? 1 : 0, total64, views);
         GS_LAUNCH_CHECK();
     }
+    // the total is complete after the FIRST kernel: it is copied to the host now and an event marks the copy, so that
+    // gs_render_count_read returns while the depth sort and the scan are still running and the caller can enqueue the
+    // duplicate / sort / blend launches behind them -- the stream never runs dry behind the operator's host sync
+    GS_CUDA_TRY(cudaMemcpyAsync(slot, total64, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    GS_CUDA_TRY(cudaEventRecord(g_count_events[slot - g_count_slots], stream));
     {
         GsStageTimer timer(GS_STAGE_SORT, stream);  // depth order of the splats (stable: ties keep index order)
         GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, dkey, dkey_sorted, index, order, P, 0, 32, stream));
@@ -225,9 +271,17 @@ extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start,
         GS_LAUNCH_CHECK();
         GS_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_temp, cub_bytes, touched_sorted, offsets, P, stream));
     }
-    unsigned long long total = 0;
-    GS_CUDA_TRY(cudaMemcpyAsync(&total, total64, sizeof(total), cudaMemcpyDeviceToHost, stream));
-    GS_CUDA_TRY(cudaStreamSynchronize(stream));
+    return GS_OK;
+}
+
+extern "C" int gs_render_count_read(void *ticket, int64_t *R_host, void *stream_) {
+    GS_REQUIRE(ticket != nullptr && R_host != nullptr, "ticket / R_host");
+    *R_host = 0;
+    (void)stream_;
+    const ptrdiff_t idx = (unsigned long long *)ticket - g_count_slots;
+    GS_REQUIRE(g_count_slots != nullptr && idx >= 0 && idx < GS_COUNT_SLOTS, "not a ticket of gs_render_count_launch");
+    GS_CUDA_TRY(cudaEventSynchronize(g_count_events[idx]));
+    const unsigned long long total = *(volatile unsigned long long *)ticket;
     if (total >= (1ull << 31)) {  // the 32-bit scan (and the int32 instance indices downstream) cannot hold it
         gs_set_error("gs_render_count: %llu splat-tile instances in one call (limit 2^31 - 1): render fewer views per call",
                      total);
@@ -235,6 +289,22 @@ extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start,
     }
     *R_host = (int64_t)total;
     return GS_OK;
+}
+
+extern "C" int gs_render_count_batched(int num_views, const int32_t *view_start, int image_height, int image_width,
+                                       const float *means2D, const float *conic_opacity, const float *rgb,
+                                       const float *depths, const int32_t *radii, const uint8_t *compute_locally,
+                                       uint32_t *order, uint32_t *offsets, float *rec, void *temp, size_t temp_bytes,
+                                       int64_t *R_host, void *stream_) {
+    GS_REQUIRE(R_host != nullptr, "R_host");
+    *R_host = 0;
+    GS_REQUIRE(view_start != nullptr, "view_start[0] must be 0");
+    void *ticket = nullptr;
+    const int rc = gs_render_count_launch(num_views, view_start, 0, image_height, image_width, means2D, conic_opacity, rgb,
+                                          depths, radii, compute_locally, order, offsets, rec, temp, temp_bytes, &ticket,
+                                          stream_);
+    if (rc != GS_OK) return rc;
+    return gs_render_count_read(ticket, R_host, stream_);
 }
 
 extern "C" int gs_render_count(int P, int image_height, int image_width, const float *means2D,

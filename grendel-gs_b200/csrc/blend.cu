@@ -254,9 +254,9 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
                 const float power = dx * (a.z * dx + a.w * dy) + b.x * dy * dy;
                 const bool ok = has && power >= b.z;  // false for NaN (finished / outside pixels)
                 if (!__any_sync(FULL, ok)) continue;
-                if (ok && power <= 0.f) {
+                if (ok && power <= 0.f) {   // thr <= power <= 0  <=>  alpha >= 1/255 (thr = ln(1/(255 opacity)), no margin)
                     const float alpha = fminf(ALPHA_MAX, b.y * gs_exp_neg(power));
-                    if (alpha >= ALPHA_MIN) {
+                    {
                         const float test_T = T * (1.f - alpha);
                         if (test_T < T_EPS) {
                             done = true;
@@ -361,7 +361,7 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
              const uint8_t *__restrict__ compute_locally, const uint2 *__restrict__ ranges,
              const uint32_t *__restrict__ ids, float *__restrict__ image, float *__restrict__ final_T,
              uint32_t *__restrict__ n_contrib, unsigned long long *__restrict__ stats, const SegWs seg) {
-    __shared__ SRec s_rec[FW_CHUNK];
+    __shared__ SRec s_rec[FW_CHUNK + 1];   // + the slot an empty candidate list points at (entry g0 + 32 of the last group)
     __shared__ uint16_t s_cull[FW_CHUNK];
     __shared__ unsigned long long s_stats[3];
     __shared__ uint32_t s_red[F2_WARPS + 2];
@@ -393,27 +393,40 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
     const p2 zero2 = p2_bc(0.f), one2 = p2_bc(1.f), mone2 = p2_bc(-1.f);
     p2 T = one2, C0 = zero2, C1 = zero2, C2 = zero2, Ct0 = zero2, Ct1 = zero2, Ct2 = zero2;
     uint32_t last0 = 0, last1 = 0, blended = 0, cons0 = 0, cons1 = 0;
-    bool done0 = !in0, done1 = !in1;
+    // a finished / outside pixel is one whose coordinate is NaN: no separate flags to maintain in the loop
+#define F2_DONE (npx0 != npx0 && npx1 != npx1)
     // this pixel pair's entries in a checkpoint slot: (8x4 block) * 32 + (row in block) * 8 + (column in block)
     float4 *ck = nullptr;
     int nck = 0;
     if (CKPT)
         ck = seg.ckpt + ((size_t)(range.x / SEG_K) + blockIdx.x) * SEG_SLOT + (warp * 2 + (lx >> 3)) * 32 + (ly & 3) * 8 + (lx & 7);
+    // a quarter warp without a candidate runs the iteration on entry g0 + clz(0) = g0 + 32 with an effective alpha of 0: whatever
+    // record sits there must be finite (0 * inf would poison the colour sums), so slots the staging never wrote start as 0
+    // (each thread clears exactly the slots it stages later: program order, no barrier)
+    for (int i = threadIdx.x; i < FW_CHUNK + 1; i += F2_THREADS) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        s_rec[i].a = z; s_rec[i].b = z; s_rec[i].c = z;
+    }
     for (int base = 0; base < total; base += FW_CHUNK) {
-        if (__syncthreads_count(done0 && done1) == F2_THREADS) break;
+        if (__syncthreads_count(F2_DONE) == F2_THREADS) break;
         const int cnt = min(FW_CHUNK, total - base);
         for (int i = threadIdx.x; i < cnt; i += F2_THREADS) {
             const uint32_t g = ids[range.x + base + i];
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-            s_rec[i].a = a; s_rec[i].b = b; s_rec[i].c = c;
+            // staged in the POSITIVE form q = -power = alpha' dx^2 + beta' dx dy + gamma' dy^2 with t = -thr >= 0: the pixel test
+            // thr <= power <= 0 becomes 0 <= q <= t, ONE unsigned compare of the bit patterns (negative, NaN and inf
+            // patterns are all above t's; q is never -0 because the non-negative gamma' dy^2 is added last)
+            s_rec[i].a = make_float4(a.x, a.y, -a.z, -a.w);
+            s_rec[i].b = make_float4(-b.x, b.y, fmaxf(-b.z, 0.f), b.w);
+            s_rec[i].c = c;
             const uint16_t m16 = (uint16_t)block_mask16(a, b, c.z, c.w, X0, Y0);
             s_cull[i] = m16;
             if (CKPT) seg.cull[range.x + base + i] = m16;
         }
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {
-            if (__all_sync(FULL, done0 && done1)) break;
+            if (__all_sync(FULL, F2_DONE)) break;
             {   // segment boundary (see k_blend_fwd)
                 const int e0 = base + g0;
                 if (e0 > 0 && (e0 & (SEG_K - 1)) == 0) {
@@ -436,32 +449,32 @@ k_blend_fwd2(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, c
             p2 npx_cur = npx;
             while (__any_sync(FULL, mine != 0u)) {
                 const bool has = mine != 0u;
-                const int lz = __clz((int)mine);       // 32 when empty
-                const int j = g0 + (has ? lz : 0);
-                mine &= ~(0x80000000u >> lz);
+                const int lz = __clz((int)mine);       // 32 when empty: a finite slot (see the clearing loop above)
+                const int j = g0 + lz;
+                mine &= ~__funnelshift_rc(0x80000000u, 0u, lz);   // (0x80000000 >> lz), 0 for lz = 32 (clamped shift)
                 const SRec *sr = &s_rec[j];
                 const float4 a = sr->a, b = sr->b;
                 const float dy = a.y - pyf;
                 const p2 dx = p2_add(p2_bc(a.x), npx_cur);
                 const float t = a.w * dy, u = b.x * dy * dy;
-                const p2 pw = p2_fma(dx, p2_fma(p2_bc(a.z), dx, p2_bc(t)), p2_bc(u));
-                const float pw0 = p2_lo(pw), pw1 = p2_hi(pw);
-                const bool ok0 = has && pw0 >= b.z, ok1 = has && pw1 >= b.z;  // false for NaN
-#ifndef F2_NO_EARLY_OUT
-                if (!__any_sync(FULL, ok0 || ok1)) continue;   // 9 % of the iterations on c2
+                const p2 pw = p2_fma(dx, p2_fma(p2_bc(a.z), dx, p2_bc(t)), p2_bc(u));   // q = -power (>= 0, or NaN)
+                const uint32_t tb = __float_as_uint(b.z);
+                const bool ok0 = has && __float_as_uint(p2_lo(pw)) <= tb, ok1 = has && __float_as_uint(p2_hi(pw)) <= tb;
+#ifdef F2_EARLY_OUT   // with the row-band culling few iterations have no passing lane: the vote costs more than it skips
+                if (!__any_sync(FULL, ok0 || ok1)) continue;   // (0.591 -> 0.581 ms on c2 without it)
 #endif
-                const p2 e = p2_mul(pw, p2_bc(1.4426950408889634f));
+                const p2 e = p2_mul(pw, p2_bc(-1.4426950408889634f));
                 float G0, G1;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G0) : "f"(p2_lo(e)));
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G1) : "f"(p2_hi(e)));
                 const p2 araw = p2_mul(p2_bc(b.y), p2_make(G0, G1));
                 const float al0 = fminf(ALPHA_MAX, p2_lo(araw)), al1 = fminf(ALPHA_MAX, p2_hi(araw));
-                const bool v0 = ok0 && pw0 <= 0.f && al0 >= ALPHA_MIN, v1 = ok1 && pw1 <= 0.f && al1 >= ALPHA_MIN;
+                const bool v0 = ok0, v1 = ok1;   // 0 <= q <= t  <=>  alpha >= 1/255: no second test on alpha
                 const p2 test_T = p2_mul(T, p2_fma(p2_make(al0, al1), mone2, one2));
                 const bool end0 = v0 && p2_lo(test_T) < T_EPS, end1 = v1 && p2_hi(test_T) < T_EPS;
                 const bool bl0 = v0 && !end0, bl1 = v1 && !end1;
-                if (end0) { done0 = true; npx0 = qnan; if (STATS) cons0 = (uint32_t)(base + j + 1); }
-                if (end1) { done1 = true; npx1 = qnan; if (STATS) cons1 = (uint32_t)(base + j + 1); }
+                if (end0) { npx0 = qnan; if (STATS) cons0 = (uint32_t)(base + j + 1); }
+                if (end1) { npx1 = qnan; if (STATS) cons1 = (uint32_t)(base + j + 1); }
                 npx_cur = p2_make(npx0, npx1);
                 // effective alpha: 0 for a pixel that does not blend this splat -- every update below is then a no-op, so
                 // the packed state needs no per-component selects (T (1 - ae) is the same product as test_T when blending)
@@ -672,7 +685,7 @@ k_blend_bwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
                     if (!__any_sync(0xffffffffu, ok)) continue;
                     const float G = gs_exp_neg(power);
                     const float alpha = fminf(ALPHA_MAX, b.y * G);
-                    ok = ok && power <= 0.f && alpha >= ALPHA_MIN;
+                    ok = ok && power <= 0.f;   // thr <= power <= 0  <=>  alpha >= 1/255
                     if (!__any_sync(0xffffffffu, ok)) continue;
                     // Per-pixel weight m = dL/dG * G; the per-splat gradients are its moments over the pixels
                     // (S0, Sx, Sy, Sxx, Sxy, Syy) plus three colour sums; they are combined with the splat's
@@ -817,7 +830,7 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
         uint32_t rstride = 0;
         float rscale = 0.f;
         if (role >= 0) {
-            if (role < 2) { rptr = d_means2D + role; rstride = 2; rscale = role == 0 ? 0.5f * (float)W : 0.5f * (float)H; }
+            if (role < 2) { rptr = d_means2D + role; rstride = 2; rscale = role == 0 ? -0.5f * (float)W : -0.5f * (float)H; }
             else if (role < 6) { rptr = d_conic_opacity + (role - 2); rstride = 4; rscale = role == 3 ? -1.f : (role == 5 ? 1.f : -0.5f); }
             else { rptr = d_rgb + (role - 6); rstride = 3; rscale = 1.f; }
         }
@@ -856,7 +869,9 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
                 const uint32_t bl = ((q < 4 ? cold.blive : cold.blive_hi) >> (8 * (q & 3))) & 0xffu;
                 if ((uint32_t)i >= bl) m &= ~(1u << q);
             }
-            s_rec[lane].a = a; s_rec[lane].b = b;
+            // positive form q = -power, t = -thr (see k_blend_fwd2's staging): the pixel test is one unsigned compare
+            s_rec[lane].a = make_float4(a.x, a.y, -a.z, -a.w);
+            s_rec[lane].b = make_float4(-b.x, b.y, fmaxf(-b.z, 0.f), b.w);
             s_rec[lane].c = make_float4(c.x, c.y, gs_rcp_approx(b.y), __uint_as_float(g));
             s_mask[lane] = m;
         }
@@ -879,12 +894,11 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
                 if (m8 & (1u << b)) {
                     const float4 pc = s_pix[b * 32];
                     const float dx = mxl - (float)((b & 1) * 8), dy = myl - (float)((b >> 1) * 4);
-                    const float power = dx * (a.z * dx + a.w * dy) + b4.x * dy * dy;
-                    const bool ok1 = (j < __float_as_int(pc.w)) && power >= b4.z && power <= 0.f;
-                    if (__any_sync(FULL, ok1)) {
-                        const float G = gs_exp_neg(power);
+                    const float q = dx * (a.z * dx + a.w * dy) + b4.x * dy * dy;   // -power
+                    const bool ok = (j < __float_as_int(pc.w)) && __float_as_uint(q) <= __float_as_uint(b4.z);
+                    if (__any_sync(FULL, ok)) {
+                        const float G = gs_exp_neg(-q);
                         const float alpha = fminf(ALPHA_MAX, b4.y * G);
-                        const bool ok = ok1 && alpha >= ALPHA_MIN;
                         const float ae = ok ? alpha : 0.f;   // effective alpha: 0 = this lane skips the splat
                         float inv;                            // 1/(1-ae), 1-ae in [0.01, 1]: one MUFU.RCP
                         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - ae));
@@ -905,6 +919,7 @@ k_blend_bwd_seg(int W, int H, int tiles_per_view, const float4 *__restrict__ rec
             if (!any_full) continue;
             {   // per-lane pre-mix (linear, commutes with the sums), so that every reduced value is ONE output element:
                 // d power/d mean = (2a'dx + b'dy, 2c'dy + b'dx); dL/dopacity = sum(m) / opacity
+                // (the staged a.z, a.w, b4.x are -a', -b', -c': the sign sits in the roles' scale factors)
                 const float sx = v[0], sy = v[1];
                 v[0] = 2.f * a.z * sx + a.w * sy;
                 v[1] = 2.f * b4.x * sy + a.w * sx;

@@ -42,6 +42,9 @@ SIGNATURES = {
     "gs_render_backward": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "gs_render_count_batched": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                      C.POINTER(_i64), _vp]),
+    "gs_render_count_launch": (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                    C.POINTER(C.c_void_p), _vp]),
+    "gs_render_count_read": (_i, [_vp, C.POINTER(_i64), _vp]),
     "gs_render_forward_batched": (_i, [_i, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gs_render_backward_batched": (_i, [_i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,

@@ -226,6 +226,40 @@ def _seg_workspace(R, num_tiles, dev, needed):
     return torch.empty((nb,), dtype=torch.uint8, device=dev), nb
 
 
+# Instance-count hints: the render reads its instance count R back from the device (the operator's one host sync, as in
+# the reference, which sizes its buffers from num_rendered).  Behind that sync the GPU is idle until the next launch, so
+# everything the launch needs is allocated BEFORE the sync from the previous call's R of the same shape (+8 %); only when
+# the hint is missing or too small are the buffers allocated after the read-back.
+_R_HINT = {}
+
+
+class _InstanceBuffers:
+    __slots__ = ("cap", "tiles", "ids", "sort_temp", "sb", "seg", "segb")
+
+    def __init__(self, cap, num_tiles, dev, needs_grad):
+        self.cap = max(int(cap), 1)
+        self.tiles = torch.empty((2, self.cap), dtype=torch.int32, device=dev)
+        self.ids = torch.empty((2, self.cap), dtype=torch.int32, device=dev)
+        self.sb = _lib.query("gs_render_sort_temp_bytes", self.cap)
+        self.sort_temp = torch.empty((self.sb,), dtype=torch.uint8, device=dev)
+        self.seg, self.segb = _seg_workspace(self.cap, num_tiles, dev, needs_grad)
+
+    def row(self, t, r):
+        return t.data_ptr() + 4 * self.cap * r
+
+
+def _instance_buffers_before_sync(key, num_tiles, dev, needs_grad):
+    est = _R_HINT.get(key)
+    return None if est is None else _InstanceBuffers(est + est // 12 + 4096, num_tiles, dev, needs_grad)
+
+
+def _instance_buffers_after_sync(key, pre, R, num_tiles, dev, needs_grad):
+    _R_HINT[key] = R
+    if pre is not None and R <= pre.cap and (R > 0 or pre.seg is None):
+        return pre
+    return _InstanceBuffers(R, num_tiles, dev, needs_grad)
+
+
 class _RenderGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2D, conic_opacity, rgb, depths, radii, compute_locally, rs, collector):
@@ -255,31 +289,33 @@ class _RenderGaussians(torch.autograd.Function):
         rec = torch.empty((max(P, 1), 12), dtype=torch.float32, device=dev)
         tb = _lib.query("gs_render_count_temp_bytes", P)
         temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
-        R = C.c_int64(0)
-        _lib.call("gs_render_count", P, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
-                  depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(),
-                  rec.data_ptr(), temp.data_ptr(), tb, C.byref(R), s)
-        R = int(R.value)
-        global LAST_R_TOTAL
-        LAST_R_TOTAL += R
-        Ra = max(R, 1)
-        tiles = torch.empty((2, Ra), dtype=torch.int32, device=dev)
-        ids = torch.empty((2, Ra), dtype=torch.int32, device=dev)
-        sb = _lib.query("gs_render_sort_temp_bytes", R)
-        sort_temp = torch.empty((sb,), dtype=torch.uint8, device=dev)
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
         image = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         final_T = torch.empty((H, W), dtype=torch.float32, device=dev)
         n_contrib = torch.empty((H, W), dtype=torch.int32, device=dev)
         stats = torch.empty((3,), dtype=torch.int64, device=dev)
-        seg, segb = _seg_workspace(R, T, dev, means2D.requires_grad or conic_opacity.requires_grad or rgb.requires_grad)
+        needs_grad = means2D.requires_grad or conic_opacity.requires_grad or rgb.requires_grad
+        R = C.c_int64(0)
+        ticket = C.c_void_p()
+        _lib.call("gs_render_count_launch", 1, None, P, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
+                  depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(),
+                  rec.data_ptr(), temp.data_ptr(), tb, C.byref(ticket), s)
+        key = (1, P, H, W, needs_grad)
+        pre = _instance_buffers_before_sync(key, T, dev, needs_grad)    # host work while the count / sort / scan run
+        _lib.call("gs_render_count_read", ticket, C.byref(R), s)   # the operator's one host sync
+        R = int(R.value)
+        global LAST_R_TOTAL
+        LAST_R_TOTAL += R
+        ib = _instance_buffers_after_sync(key, pre, R, T, dev, needs_grad)
+        seg = ib.seg if R > 0 else None
         _lib.call("gs_render_forward", P, R, H, W, means2D.data_ptr(), radii.data_ptr(), cl.data_ptr(),
-                  order.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), tiles[0].data_ptr(),
-                  ids[0].data_ptr(), tiles[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(),
-                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), _lib.ptr(seg), segb, s)
+                  order.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), ib.row(ib.tiles, 0),
+                  ib.row(ib.ids, 0), ib.row(ib.tiles, 1), ib.row(ib.ids, 1), ib.sort_temp.data_ptr(), ib.sb, ranges.data_ptr(),
+                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), _lib.ptr(seg),
+                  ib.segb if seg is not None else 0, s)
         ev1.record()
         _timed(collector, "forward_render_time", ev0, ev1)
-        ids_sorted = ids[1].clone() if R > 0 else ids[1]  # let the 2R-entry scratch go back to the allocator
+        ids_sorted = ib.ids[1]    # a view: the (tile, id) scratch stays alive until the backward has run (16 B / instance)
         ctx.rs, ctx.R, ctx.P, ctx.collector, ctx.seg = rs, R, P, collector, seg
         ctx.save_for_backward(rec, bg, cl, ranges, ids_sorted, final_T, n_contrib)
         n_render, n_consider, n_contrib_sum = stats[0], stats[1], stats[2]
@@ -376,31 +412,33 @@ class _RenderGaussiansBatched(torch.autograd.Function):
         rec = torch.empty((max(P, 1), 12), dtype=torch.float32, device=dev)
         tb = _lib.query("gs_render_count_temp_bytes", P)
         temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
-        R = C.c_int64(0)
-        _lib.call("gs_render_count_batched", B, vs, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
-                  depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(),
-                  rec.data_ptr(), temp.data_ptr(), tb, C.byref(R), s)
-        R = int(R.value)
-        global LAST_R_TOTAL
-        LAST_R_TOTAL += R
-        Ra = max(R, 1)
-        tiles = torch.empty((2, Ra), dtype=torch.int32, device=dev)
-        ids = torch.empty((2, Ra), dtype=torch.int32, device=dev)
-        sb = _lib.query("gs_render_sort_temp_bytes", R)
-        sort_temp = torch.empty((sb,), dtype=torch.uint8, device=dev)
         ranges = torch.empty((B * T, 2), dtype=torch.int32, device=dev)
         image = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
         final_T = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         n_contrib = torch.empty((B, H, W), dtype=torch.int32, device=dev)
         stats = torch.empty((B, 3), dtype=torch.int64, device=dev)
-        seg, segb = _seg_workspace(R, B * T, dev, means2D.requires_grad or conic_opacity.requires_grad or rgb.requires_grad)
+        needs_grad = means2D.requires_grad or conic_opacity.requires_grad or rgb.requires_grad
+        R = C.c_int64(0)
+        ticket = C.c_void_p()
+        _lib.call("gs_render_count_launch", B, vs, P, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
+                  depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(),
+                  rec.data_ptr(), temp.data_ptr(), tb, C.byref(ticket), s)
+        key = (B, P, H, W, needs_grad)
+        pre = _instance_buffers_before_sync(key, B * T, dev, needs_grad)   # host work while the count / sort / scan run
+        _lib.call("gs_render_count_read", ticket, C.byref(R), s)    # the operator's one host sync
+        R = int(R.value)
+        global LAST_R_TOTAL
+        LAST_R_TOTAL += R
+        ib = _instance_buffers_after_sync(key, pre, R, B * T, dev, needs_grad)
+        seg = ib.seg if R > 0 else None
         _lib.call("gs_render_forward_batched", B, vs, R, H, W, means2D.data_ptr(), radii.data_ptr(), cl.data_ptr(),
-                  order.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), tiles[0].data_ptr(),
-                  ids[0].data_ptr(), tiles[1].data_ptr(), ids[1].data_ptr(), sort_temp.data_ptr(), sb, ranges.data_ptr(),
-                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), _lib.ptr(seg), segb, s)
+                  order.data_ptr(), offsets.data_ptr(), rec.data_ptr(), bg.data_ptr(), ib.row(ib.tiles, 0),
+                  ib.row(ib.ids, 0), ib.row(ib.tiles, 1), ib.row(ib.ids, 1), ib.sort_temp.data_ptr(), ib.sb, ranges.data_ptr(),
+                  image.data_ptr(), final_T.data_ptr(), n_contrib.data_ptr(), stats.data_ptr(), _lib.ptr(seg),
+                  ib.segb if seg is not None else 0, s)
         ev1.record()
         _timed(collector, "forward_render_time", ev0, ev1)
-        ids_sorted = ids[1].clone() if R > 0 else ids[1]  # let the 2R-entry scratch go back to the allocator
+        ids_sorted = ib.ids[1]    # a view: the (tile, id) scratch stays alive until the backward has run (16 B / instance)
         ctx.rs, ctx.R, ctx.P, ctx.B, ctx.collector, ctx.seg = rs, R, P, B, collector, seg
         ctx.save_for_backward(rec, bg, cl, ranges, ids_sorted, final_T, n_contrib)
         ctx.mark_non_differentiable(stats)

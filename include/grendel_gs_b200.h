@@ -204,6 +204,18 @@ GS_API int gs_render_count_batched(int num_views, const int32_t *view_start_host
                                    const float *depths, const int32_t *radii, const uint8_t *compute_locally,
                                    uint32_t *order, uint32_t *offsets, float *rec, void *temp, size_t temp_bytes,
                                    int64_t *R_host, void *stream);
+/* The count in two halves.  gs_render_count_launch enqueues stages 21-24 + 30 (view_start_host = NULL, P = number of splats:
+ * the single-camera form; otherwise P is ignored and the total is view_start_host[num_views]) and hands back a ticket;
+ * gs_render_count_read blocks until the instance total -- complete after the FIRST kernel -- has reached the host and
+ * returns it, while the depth sort and the scan are still running: the caller sizes its buffers and enqueues
+ * gs_render_forward behind them, so the stream does not run dry behind the operator's one host sync
+ * (the reference syncs on num_rendered the same way; gaussian_renderer/__init__.py:1271-1282).  At most 64 tickets may be
+ * outstanding.  gs_render_count / gs_render_count_batched = launch + read. */
+GS_API int gs_render_count_launch(int num_views, const int32_t *view_start_host, int P, int image_height, int image_width,
+                                  const float *means2D, const float *conic_opacity, const float *rgb, const float *depths,
+                                  const int32_t *radii, const uint8_t *compute_locally, uint32_t *order, uint32_t *offsets,
+                                  float *rec, void *temp, size_t temp_bytes, void **ticket, void *stream);
+GS_API int gs_render_count_read(void *ticket, int64_t *R_host, void *stream);
 GS_API int gs_render_forward_batched(int num_views, const int32_t *view_start_host, int64_t R, int image_height,
                                      int image_width, const float *means2D, const int32_t *radii,
                                      const uint8_t *compute_locally, const uint32_t *order, const uint32_t *offsets,

@@ -17,6 +17,10 @@ WANT = [
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe %"),
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe %"),
     ("sm__inst_executed_pipe_xu.sum", "XU (MUFU) instructions"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe %"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe (instructions) %"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared data-pipe wavefronts % of peak"),
+    ("smsp__warps_eligible.avg.per_cycle_active", "eligible warps / scheduler / cycle"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("launch__registers_per_thread", "registers / thread"),
@@ -40,6 +44,16 @@ def main():
             if key in hdr:
                 i = hdr.index(key)
                 print(f"| {label} (`{key}`) | {r[i]} {units[i]} |")
+        stalls = []
+        for i, k in enumerate(hdr):
+            if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and "not_issued" not in k:
+                try:
+                    stalls.append((float(r[i].replace(",", "")), k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        if stalls:
+            top = ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:6])
+            print(f"| warps stalled per issue, top reasons | {top} |")
         i0, i1 = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         try:
             tot = float(r[i0]) + float(r[i1])

@@ -19,7 +19,7 @@ from gs_b200 import synthetic as syn  # noqa: E402
 from oracle.oracle import Oracle      # noqa: E402
 
 F = np.float32
-THR_MARGIN = F(0.02)
+THR_MARGIN = F(0.0)    # k_count_tiles: thr = ln(1/(255 opacity)), the exponent test IS the alpha >= 1/255 test
 ABS_MARGIN = F(0.05)
 
 

@@ -70,6 +70,10 @@ def test_argument_errors_are_reported_not_crashed(lib):
         ("gs_render_count_batched", (0, one, 16, 16, None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(R), None)),
         ("gs_render_count_batched", (65, one, 16, 16, None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(R), None)),
         ("gs_render_count_batched", (1, (i32 * 2)(3, 5), 16, 16, None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(R), None)),
+        ("gs_render_count_launch", (2, None, 4, 16, 16, None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(vp()), None)),
+        ("gs_render_count_launch", (1, None, 4, 16, 16, None, None, None, None, None, None, None, None, None, None, 0, None, None)),
+        ("gs_render_count_read", (None, ctypes.byref(R), None)),
+        ("gs_render_count_read", (ctypes.cast(ctypes.byref(R), vp), ctypes.byref(R), None)),   # not a ticket of the library
         ("gs_render_backward_batched", (0, 0, 0, 16, 16, None, None, None, None, None, None, None, None, None, 0, None, None, None, None)),
         ("gs_loss_forward_batched", (1, 16, 16, None, None, None, None, None, 0, None)),
         ("gs_xchg_pack_p2p", (0, 4, 2, None, None, None, None, None, None, None, None, None, None)),

@@ -665,7 +665,7 @@ def test_full_size_properties_config_c2():
         assert bool((a1[pre["radii"] == 0] == 0).all())
 
 
-def test_needle_splats_survive_block_culling(o32):
+def test_needle_splats_survive_block_culling(o32, o64):
     """Adversarial case for the per-block culling: sub-pixel-wide splats hundreds to thousands of pixels long at
     arbitrary angles (conic determinant dominated by cancellation).  The culling must stay conservative: image and
     gradients still match the oracle, which walks every (pixel, splat) pair."""
