@@ -1003,9 +1003,13 @@ extern "C" int gs_render_backward_batched(int num_views, int P, int64_t R, int i
     GS_REQUIRE(P >= 0 && R >= 0 && image_height > 0 && image_width > 0, "sizes");
     if (P == 0) return GS_OK;
     GS_REQUIRE(dL_dmeans2D && dL_dconic_opacity && dL_drgb, "null output");
-    GS_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 2 * (size_t)P, stream));
-    GS_CUDA_TRY(cudaMemsetAsync(dL_dconic_opacity, 0, sizeof(float) * 4 * (size_t)P, stream));
-    GS_CUDA_TRY(cudaMemsetAsync(dL_drgb, 0, sizeof(float) * 3 * (size_t)P, stream));
+    if (dL_dmeans2D == dL_dconic_opacity + 4 * (size_t)P && dL_drgb == dL_dmeans2D + 2 * (size_t)P) {
+        GS_CUDA_TRY(cudaMemsetAsync(dL_dconic_opacity, 0, sizeof(float) * 9 * (size_t)P, stream));   // one block (ops._grad_block)
+    } else {
+        GS_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 2 * (size_t)P, stream));
+        GS_CUDA_TRY(cudaMemsetAsync(dL_dconic_opacity, 0, sizeof(float) * 4 * (size_t)P, stream));
+        GS_CUDA_TRY(cudaMemsetAsync(dL_drgb, 0, sizeof(float) * 3 * (size_t)P, stream));
+    }
     if (R == 0) return GS_OK;
     GS_REQUIRE(rec && bg && compute_locally && ranges && ids_sorted && final_T && n_contrib && dL_dimage, "null input");
     const int gx = (image_width + GS_BLOCK_X - 1) / GS_BLOCK_X, gy = (image_height + GS_BLOCK_Y - 1) / GS_BLOCK_Y;

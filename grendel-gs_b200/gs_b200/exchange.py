@@ -292,6 +292,7 @@ class _ExchangeSplats(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, state, m2, rgb, co):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         layout, group = state["layout"], state["group"]
         B, P, W = state["B"], state["P"], state["W"]
         m2, rgb, co = m2.contiguous(), rgb.contiguous(), co.contiguous()
@@ -379,6 +380,7 @@ class _ExchangeSplatsDirect(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, state, m2, rgb, co):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         B, peer = state["B"], state["peer"]
         N = state["view_start"][B]
         (v_m2, v_rgb, v_co, v_rad, v_dep), _ = peer.views()

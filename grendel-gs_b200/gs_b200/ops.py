@@ -96,6 +96,7 @@ def _timed(collector, key, start, end):
 class _PreprocessGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, scales, rotations, shs, opacities, rs):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         means3D, scales, rotations = _f32c(means3D, "means3D"), _f32c(scales, "scales"), _f32c(rotations, "rotations")
         shs, opacities = _f32c(shs, "shs"), _f32c(opacities, "opacities")
         P = means3D.shape[0]
@@ -159,6 +160,7 @@ class _PreprocessGaussiansRaw(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, f_dc, f_rest, scaling, rotation, opacity, rs):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         xyz, f_dc, f_rest = _f32c(xyz, "_xyz"), _f32c(f_dc, "_features_dc"), _f32c(f_rest, "_features_rest")
         scaling, rotation, opacity = _f32c(scaling, "_scaling"), _f32c(rotation, "_rotation"), _f32c(opacity, "_opacity")
         P = xyz.shape[0]
@@ -260,9 +262,17 @@ def _instance_buffers_after_sync(key, pre, R, num_tiles, dev, needs_grad):
     return _InstanceBuffers(R, num_tiles, dev, needs_grad)
 
 
+def _grad_block(P, dev):
+    """dL/dmeans2D (P,2), dL/dconic_opacity (P,4), dL/drgb (P,3) as consecutive blocks of ONE allocation: the backward
+    zeroes them with one memset instead of three (it accumulates into them with RED.ADD)."""
+    buf = torch.empty((9 * max(P, 1),), dtype=torch.float32, device=dev)   # conic first: its rows are read as float4
+    return buf[4 * P:6 * P].view(P, 2), buf[:4 * P].view(P, 4), buf[6 * P:9 * P].view(P, 3)
+
+
 class _RenderGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2D, conic_opacity, rgb, depths, radii, compute_locally, rs, collector):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         means2D, conic_opacity, rgb = _f32c(means2D, "means2D"), _f32c(conic_opacity, "conic_opacity"), _f32c(rgb, "rgb")
         depths = _f32c(depths, "depths")
         if radii.dtype != torch.int32:
@@ -329,9 +339,7 @@ class _RenderGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         dev = rec.device
         g_image = torch.zeros((3, H, W), dtype=torch.float32, device=dev) if g_image is None else _f32c(g_image, "grad")
-        d_means2D = torch.empty((P, 2), dtype=torch.float32, device=dev)
-        d_conic = torch.empty((P, 4), dtype=torch.float32, device=dev)
-        d_rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        d_means2D, d_conic, d_rgb = _grad_block(P, dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         seg = ctx.seg
@@ -380,6 +388,7 @@ class _RenderGaussiansBatched(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2D, conic_opacity, rgb, depths, radii, compute_locally, view_start, rs, collector):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         means2D, conic_opacity, rgb = _f32c(means2D, "means2D"), _f32c(conic_opacity, "conic_opacity"), _f32c(rgb, "rgb")
         depths = _f32c(depths, "depths")
         if radii.dtype != torch.int32:
@@ -451,9 +460,7 @@ class _RenderGaussiansBatched(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         dev = rec.device
         g_image = torch.zeros((B, 3, H, W), dtype=torch.float32, device=dev) if g_image is None else _f32c(g_image, "grad")
-        d_means2D = torch.empty((P, 2), dtype=torch.float32, device=dev)
-        d_conic = torch.empty((P, 4), dtype=torch.float32, device=dev)
-        d_rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        d_means2D, d_conic, d_rgb = _grad_block(P, dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         seg = ctx.seg
@@ -484,6 +491,7 @@ def render_gaussians_batched(means2D, conic_opacity, rgb, depths, radii, compute
 class _FusedL1SSIMBatched(torch.autograd.Function):
     @staticmethod
     def forward(ctx, images, gts, rows4):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         images = _f32c(images, "images")
         B, _, H, W = images.shape
         if len(gts) != B or len(rows4) != B:
@@ -515,6 +523,8 @@ class _FusedL1SSIMBatched(torch.autograd.Function):
     def backward(ctx, g_out):
         images, temp = ctx.saved_tensors
         B, _, H, W = images.shape
+        if g_out is None:
+            return None, None, None
         g_l1, g_ssim = g_out[:, 0].to(torch.float32).contiguous(), g_out[:, 1].to(torch.float32).contiguous()
         d_images = torch.empty_like(images)
         gptr = (C.c_void_p * B)(*[None if g is None else g.data_ptr() for g in ctx.gts])
@@ -571,6 +581,7 @@ class _FusedL1SSIM(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, image, gt_u8, row0, row1, crow0, crow1):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         image = _f32c(image, "image")
         if gt_u8.dtype != torch.uint8 or not gt_u8.is_cuda:
             raise TypeError("gt strip must be a CUDA uint8 tensor (3, rows, W)")
@@ -613,6 +624,60 @@ def fused_l1_ssim(image, gt_u8, row0, row1, count_row0=None, count_row1=None):
     return _FusedL1SSIM.apply(image, gt_u8, int(row0), int(row1), c0, c1)
 
 
+_LOSS_W = {}
+
+
+class _FusedLoss(torch.autograd.Function):
+    """(1 - lambda) Ll1 + lambda (1 - ssim) of one strip as ONE autograd node (train_internal.py:166-189 forms it with five
+    elementwise kernels and as many in the backward): the two sums come out of gs_loss_forward, the combination is one dot
+    product with a cached weight vector, and the backward hands (g (1 - lambda), -g lambda) to gs_loss_backward."""
+
+    @staticmethod
+    def forward(ctx, image, gt_u8, row0, row1, crow0, crow1, lambda_dssim):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
+        image = _f32c(image, "image")
+        if gt_u8.dtype != torch.uint8 or not gt_u8.is_cuda:
+            raise TypeError("gt strip must be a CUDA uint8 tensor (3, rows, W)")
+        gt_u8 = gt_u8.contiguous()
+        _, H, W = image.shape
+        rows = row1 - row0
+        if tuple(gt_u8.shape) != (3, rows, W):
+            raise ValueError(f"gt strip must be (3,{rows},{W}), got {tuple(gt_u8.shape)}")
+        key = (image.device, float(lambda_dssim))
+        if key not in _LOSS_W:
+            _LOSS_W[key] = torch.tensor([1.0 - lambda_dssim, -lambda_dssim], dtype=torch.float32, device=image.device)
+        w = _LOSS_W[key]
+        tb = _lib.query("gs_loss_temp_bytes", rows, W)
+        temp = torch.empty((tb,), dtype=torch.uint8, device=image.device)
+        out = torch.empty((2,), dtype=torch.float32, device=image.device)
+        _lib.call("gs_loss_forward", H, W, row0, row1, crow0, crow1, image.data_ptr(), gt_u8.data_ptr(), out.data_ptr(),
+                  temp.data_ptr(), tb, _stream())
+        ctx.rows, ctx.w = (row0, row1, crow0, crow1), w
+        ctx.save_for_backward(image, gt_u8, temp)
+        return torch.dot(out, w) + float(lambda_dssim)
+
+    @staticmethod
+    def backward(ctx, g):
+        image, gt_u8, temp = ctx.saved_tensors
+        _, H, W = image.shape
+        row0, row1, crow0, crow1 = ctx.rows
+        if g is None:
+            return None, None, None, None, None, None, None
+        gw = (g.to(torch.float32) * ctx.w).contiguous()      # (g (1 - lambda), -g lambda)
+        d_image = torch.empty_like(image)
+        _lib.call("gs_loss_backward", H, W, row0, row1, crow0, crow1, image.data_ptr(), gt_u8.data_ptr(),
+                  temp.data_ptr(), gw.data_ptr(), gw.data_ptr() + 4, d_image.data_ptr(), _stream())
+        return d_image, None, None, None, None, None, None
+
+
+def fused_loss(image, gt_u8, row0, row1, lambda_dssim, count_row0=None, count_row1=None):
+    """-> 0-dim loss (1 - lambda) Ll1 + lambda (1 - ssim) of the strip rows [row0, row1) (same window / count-row
+    semantics as fused_l1_ssim)."""
+    c0 = int(row0) if count_row0 is None else int(count_row0)
+    c1 = int(row1) if count_row1 is None else int(count_row1)
+    return _FusedLoss.apply(image, gt_u8, int(row0), int(row1), c0, c1, float(lambda_dssim))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # legacy tile-mask / tile-exchange helpers (SURVEY.md 8a rows L3-L4; never called by the shipped trainer)
 # ---------------------------------------------------------------------------------------------------------
@@ -647,6 +712,7 @@ def get_pixels_compute_locally_and_in_rect(compute_locally, image_height, image_
 class _LoadImageTilesByPos(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rect, pos, H, W, pixels_rect, tiles_rect):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         rect = _f32c(rect, "local_image_rect")
         pos = pos.to(device=rect.device, dtype=torch.int64).contiguous().reshape(-1, 2)
         n = pos.shape[0]
@@ -662,6 +728,8 @@ class _LoadImageTilesByPos(torch.autograd.Function):
     def backward(ctx, g):
         (pos,) = ctx.saved_tensors
         rh, rw, y0, x0, H, W = ctx.meta
+        if g is None:
+            return None, None, None, None, None, None
         g = _f32c(g, "grad")
         out = torch.zeros((3, rh, rw), dtype=torch.float32, device=g.device)
         _lib.call("gs_image_tiles_scatter_add", pos.shape[0], pos.data_ptr(), g.data_ptr(), rh, rw, y0, x0, H, W,
@@ -672,6 +740,7 @@ class _LoadImageTilesByPos(torch.autograd.Function):
 class _MergeImageTilesByPos(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, tiles, H, W, pixels_rect, tiles_rect):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         tiles = _f32c(tiles, "tiles")
         pos = pos.to(device=tiles.device, dtype=torch.int64).contiguous().reshape(-1, 2)
         rh, rw = int(pixels_rect[1]) - int(pixels_rect[0]), int(pixels_rect[3]) - int(pixels_rect[2])
@@ -686,6 +755,8 @@ class _MergeImageTilesByPos(torch.autograd.Function):
     def backward(ctx, g):
         (pos,) = ctx.saved_tensors
         rh, rw, y0, x0, H, W = ctx.meta
+        if g is None:
+            return None, None, None, None, None, None
         g = _f32c(g, "grad")
         n = pos.shape[0]
         tiles = torch.empty((n, 3, BLOCK_Y, BLOCK_X), dtype=torch.float32, device=g.device)
@@ -727,6 +798,7 @@ def pack_cameras(settings_list):
 class _PreprocessBatched(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, f_dc, f_rest, scaling, rotation, opacity, cams, meta):
+        ctx.set_materialize_grads(False)   # undefined output gradients arrive as None, not as zero-filled tensors
         xyz, f_dc, f_rest = _f32c(xyz, "_xyz"), _f32c(f_dc, "_features_dc"), _f32c(f_rest, "_features_rest")
         scaling, rotation, opacity = _f32c(scaling, "_scaling"), _f32c(rotation, "_rotation"), _f32c(opacity, "_opacity")
         cams = _f32c(cams, "cams")

@@ -99,8 +99,7 @@ def train_step_single(params, dcam, gt_u8_dev, lambda_dssim=0.2, collector=None,
         params.get_xyz, params.get_scaling, params.get_rotation, params.get_features, params.get_opacity, rs, cuda_args)
     means2D.retain_grad()
     image, *_ = ops.render_gaussians(means2D, conic_opacity, rgb, depths, radii, compute_locally, rs, cuda_args)
-    l1, ss = ops.fused_l1_ssim(image, gt_u8_dev, 0, dcam.image_height)
-    loss = (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - ss)
+    loss = ops.fused_loss(image, gt_u8_dev, 0, dcam.image_height, lambda_dssim)
     loss.backward()
     return loss, means2D, radii
 
@@ -312,7 +311,8 @@ class Trainer:
             view_start = [k * Pn for k in range(B + 1)]
         else:
             redistributed = screen
-        self._radii_local = batched[3] if batched is not None else torch.stack([s[3] for s in screen])
+        self._radii_local = (batched[3] if batched is not None else
+                             screen[0][3].unsqueeze(0) if len(screen) == 1 else torch.stack([s[3] for s in screen]))
         self._mark("x5 unpack")
         loss_sum = None
         Vp = Pl = 0
@@ -375,7 +375,7 @@ class Trainer:
             if self.border_exchange and self.world > 1 and len(st.gpu_ids) > 1:
                 from . import border
                 image, (r0, r1), _ = border.add_remote_border_rows(image, st, self.H, self.group)
-                l1, ss = ops_.fused_l1_ssim(image, self.gts_dev[k][:, r0:r1, :].contiguous(), r0, r1, y0, y1)
+                loss = ops_.fused_loss(image, self.gts_dev[k][:, r0:r1, :].contiguous(), r0, r1, self.lambda_dssim, y0, y1)
             else:
                 if resident:
                     gt = self._gt_strip(k, y0, y1, True)
@@ -383,8 +383,7 @@ class Trainer:
                     gt, ev = gt_ready[k]
                     torch.cuda.current_stream().wait_event(ev)
                     gt.record_stream(torch.cuda.current_stream())
-                l1, ss = ops_.fused_l1_ssim(image, gt, y0, y1)
-            loss = (1.0 - self.lambda_dssim) * l1 + self.lambda_dssim * (1.0 - ss)
+                loss = ops_.fused_loss(image, gt, y0, y1, self.lambda_dssim)
             loss_sum = loss if loss_sum is None else loss_sum + loss
             Vp += m2.shape[0]
             Pl += (y1 - y0) * self.W

@@ -762,3 +762,21 @@ def test_block_cull_is_invisible(o32, shape):
         a, b = got[k].double(), got0[k].double()
         tol = 1e-5 * b.abs() + 1e-5 * b.abs().mean()
         assert float(((a - b).abs() > tol).double().mean()) <= 1e-4, f"block culling changed dL/d{k}"
+
+
+def test_fused_loss_node_equals_the_two_term_form():
+    """ops.fused_loss (one autograd node) == (1 - lambda) Ll1 + lambda (1 - ssim) built from ops.fused_l1_ssim, value and
+    image gradient, on a strip with a counted sub-window."""
+    from gs_b200 import ops
+    H, W, lam = 96, 160, 0.2
+    g = torch.Generator(device="cuda").manual_seed(5)
+    gt = torch.randint(0, 256, (3, 48, W), dtype=torch.uint8, device="cuda", generator=g)
+    x1 = torch.rand((3, H, W), device="cuda", generator=g).requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    l1, ss = ops.fused_l1_ssim(x1, gt, 16, 64, 21, 59)
+    a = (1.0 - lam) * l1 + lam * (1.0 - ss)
+    b = ops.fused_loss(x2, gt, 16, 64, lam, 21, 59)
+    (3.0 * a).backward()
+    (3.0 * b).backward()
+    assert abs(float(a) - float(b)) <= 1e-6 * abs(float(a))
+    assert torch.allclose(x1.grad, x2.grad, rtol=1e-5, atol=1e-9)
