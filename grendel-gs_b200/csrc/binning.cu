@@ -138,14 +138,25 @@ k_duplicate(int P, int W, int H, const float *__restrict__ means2D, const int32_
         }
 }
 
-// Stage 60: [start,end) of every tile in the sorted list.
+// Stage 60: [start,end) of every tile in the sorted list.  One thread per TILE finds its two boundaries by binary search
+// (2 x ~23 dependent L2 reads for T = 8160 threads) instead of one thread per INSTANCE comparing neighbours (R = 5.7 M
+// threads, 18 us on c2); every tile is written -- (0,0) when it is empty, as the neighbour compare left it -- so the
+// ranges need no memset.
+GS_D uint32_t lower_bound_u32(const uint32_t *__restrict__ keys, uint32_t n, uint32_t v) {
+    uint32_t lo = 0, hi = n;   // first index with keys[index] >= v
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(keys + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
 __global__ void __launch_bounds__(BIN_THREADS)
-k_tile_ranges(int64_t R, const uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ ranges) {
-    const int64_t k = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x;
-    if (k >= R) return;
-    const uint32_t t = tile_keys[k];
-    if (k == 0 || t != tile_keys[k - 1]) ranges[2 * t] = (uint32_t)k;
-    if (k == R - 1 || t != tile_keys[k + 1]) ranges[2 * t + 1] = (uint32_t)(k + 1);
+k_tile_ranges(int64_t R, int T, const uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ ranges) {
+    const int t = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (t >= T) return;
+    const uint32_t a = lower_bound_u32(tile_keys, (uint32_t)R, (uint32_t)t);
+    const uint32_t b = lower_bound_u32(tile_keys, (uint32_t)R, (uint32_t)t + 1u);
+    reinterpret_cast<uint2 *>(ranges)[t] = a < b ? make_uint2(a, b) : make_uint2(0u, 0u);
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -356,7 +367,8 @@ extern "C" int gs_render_forward_batched(int num_views, const int32_t *view_star
     }
     const int P = views.start[num_views];
     const int T = gx * gy * num_views;  // tiles of all views
-    GS_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * (size_t)T, stream));
+    GS_REQUIRE(ranges != nullptr && ((uintptr_t)ranges & 7) == 0, "ranges must be 8-byte aligned");
+    if (R == 0) GS_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * (size_t)T, stream));
     if (R > 0) {
         GS_REQUIRE(means2D && radii && order && offsets && rec && tiles_unsorted && ids_unsorted && tiles_sorted &&
                        ids_sorted && sort_temp,
@@ -379,7 +391,7 @@ extern "C" int gs_render_forward_batched(int num_views, const int32_t *view_star
         }
         {
             GsStageTimer timer(GS_STAGE_RANGES, stream);
-            k_tile_ranges<<<(unsigned)((R + BIN_THREADS - 1) / BIN_THREADS), BIN_THREADS, 0, stream>>>(R, tiles_sorted, ranges);
+            k_tile_ranges<<<(T + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, stream>>>(R, T, tiles_sorted, ranges);
             GS_LAUNCH_CHECK();
         }
     }

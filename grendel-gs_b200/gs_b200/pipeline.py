@@ -115,14 +115,19 @@ class Trainer:
     def __init__(self, scene, cams, gts_pinned, device, rank=0, world=1, lambda_dssim=0.2, group=None,
                  fused_activations=True, border_exchange=False, batched_render=True, peer_exchange=None,
                  peer_cap_rows=None, shard=None, load_balance=True, heuristic_decay=0.0,
-                 distributed_dataset_storage=False):
+                 distributed_dataset_storage=False, feedback_lag=None):
         """scene: the WHOLE scene (sliced here into this rank's contiguous shard), or -- shard=(lo, hi, n_total) -- only
         this rank's Gaussians [lo, hi) of an n_total-Gaussian scene (synthetic.make_scene_shard).
         load_balance: feed the measured render times back into the strip division after every step
         (finish_strategy_final, workload_division.py:944-998; only where the reference's gate enables it).
         distributed_dataset_storage: only rank 0 holds the ground-truth images (gts_pinned may be None elsewhere); the
         strips of a resident=False step are scattered from rank 0's GPU (loss_distribution.py:2395-2533, gt_scatter.py)
-        instead of being read from every rank's own host copy."""
+        instead of being read from every rank's own host copy.
+        feedback_lag: the timing feedback of step k uses the render times of step k - feedback_lag.  0 = the reference's
+        sequencing (finish_strategy_final right after the step: the host waits for the device at the end of every step and
+        cannot enqueue ahead); 1 (default, GS_B200_FEEDBACK_LAG) = the times of the PREVIOUS step, whose events have
+        completed, exchanged by a host-side (gloo) all-gather that never touches the CUDA streams -- the strips move one
+        step later and the device never waits for the host."""
         from . import exchange as _ex
         self._ex = _ex
         # splat / gradient rows travel by direct NVLink stores from the pack kernels (exchange.PeerBuffers) instead of
@@ -155,6 +160,20 @@ class Trainer:
             self.params = GaussianParams(scene, device)
         self.n_local, self.n_total = hi - lo, n
         self.load_balance, self.heuristic_decay = load_balance, heuristic_decay
+        if feedback_lag is None:
+            import os as _os
+            feedback_lag = int(_os.environ.get("GS_B200_FEEDBACK_LAG", "1"))
+        self.feedback_lag = max(0, int(feedback_lag))
+        self._pending_feedback = []
+        self._fb_group = None
+        if world > 1 and load_balance and self.feedback_lag > 0:
+            import torch.distributed as _dist
+            if _dist.get_backend(group) != "gloo":   # times travel host to host: no CUDA stream is synchronised for them
+                import os as _os
+                if _os.environ.get("MASTER_ADDR", "") in ("127.0.0.1", "localhost") and "GLOO_SOCKET_IFNAME" not in _os.environ:
+                    _os.environ["GLOO_SOCKET_IFNAME"] = "lo"   # single-node rendezvous: the hostname may not resolve
+                ranks = list(range(world)) if group is None else _dist.get_process_group_ranks(group)
+                self._fb_group = _dist.new_group(ranks=ranks, backend="gloo")
         self.iteration = 0
         self.balance_log = []      # (iteration, division rows of camera 0) whenever the division moved
         self.dcams = [DeviceCamera(c, device) for c in cams]
@@ -411,10 +430,19 @@ class Trainer:
         B = len(strategies)
         if not (self.load_balance and self.world > 1 and
                 heuristics_update_enabled(self.iteration, self.world, B, self.H, self.W)):
+            self._pending_feedback.clear()
             return
+        iteration, n_renders = self.iteration, self._n_renders
+        if self.feedback_lag > 0:
+            # this step's events are still in flight: queue it, and feed back the step that is feedback_lag steps old
+            self._pending_feedback.append((strategies, collectors, iteration, n_renders))
+            if len(self._pending_feedback) <= self.feedback_lag:
+                return
+            strategies, collectors, iteration, n_renders = self._pending_feedback.pop(0)
+            B = len(strategies)
         mine = [-1.0] * B
         rows = [(st.local_rows()[1] - st.local_rows()[0]) if st.local_rows() is not None else 0 for st in strategies]
-        if self._n_renders == 1 and sum(1 for r in rows if r) > 1:
+        if n_renders == 1 and sum(1 for r in rows if r) > 1:
             # one batched render served all local strips: its time is apportioned by strip height (the reference times
             # every camera's render separately, render_final __init__.py:1217-1288)
             t = running_time_of(collectors[0])
@@ -426,11 +454,17 @@ class Trainer:
                 if r:
                     c = collectors[k] if "forward_render_time" in collectors[k] else collectors[0]
                     mine[k] = running_time_of(c)
-        loc = torch.tensor(mine, dtype=torch.float32, device=self.device)
-        allt = torch.empty((self.world * B,), dtype=torch.float32, device=self.device)
-        dist.all_gather_into_tensor(allt, loc, group=self.group)
-        times = allt.reshape(self.world, B).cpu().tolist()       # gpu_camera_running_time[gpu][camera]
-        finish_strategy(self.history, strategies, times, self.iteration, self.world, self.H, self.W, self.heuristic_decay)
+        if self.feedback_lag > 0 and (self._fb_group is not None or dist.get_backend(self.group) == "gloo"):
+            loc = torch.tensor(mine, dtype=torch.float32)          # host tensors over gloo
+            parts = [torch.empty_like(loc) for _ in range(self.world)]
+            dist.all_gather(parts, loc, group=self._fb_group if self._fb_group is not None else self.group)
+            times = torch.stack(parts).tolist()
+        else:
+            loc = torch.tensor(mine, dtype=torch.float32, device=self.device)
+            allt = torch.empty((self.world * B,), dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(allt, loc, group=self.group)
+            times = allt.reshape(self.world, B).cpu().tolist()       # gpu_camera_running_time[gpu][camera]
+        finish_strategy(self.history, strategies, times, iteration, self.world, self.H, self.W, self.heuristic_decay)
 
     GROUP_OF = {"xyz": "_xyz", "f_dc": "_features_dc", "f_rest": "_features_rest", "opacity": "_opacity",
                 "scaling": "_scaling", "rotation": "_rotation"}

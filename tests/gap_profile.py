@@ -2,7 +2,8 @@
 timeline), takes the last steps and prints every gap between consecutive GPU activities longer than 4 us with the
 activities on both sides, plus busy / idle totals per step.  No nsys in the image; this is the substitute.
 
-    python tests/gap_profile.py [--views 1] [--steps 6]            (one GPU; writes gpurun_out/gap_profile.txt)
+    python tests/gap_profile.py [--views 1] [--steps 6]            (one GPU; writes gpurun_out/gap_profile_*.txt)
+    torchrun --nproc-per-node N tests/gap_profile.py --views N     (N ranks; rank 0's timeline is reported)
 """
 import argparse
 import os
@@ -21,12 +22,18 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--e2e", action="store_true")
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     W, H, N = 1920, 1080, 2_000_000
     scene = syn.make_scene(N, W, H)
     cams = syn.make_batch_cameras(W, H, a.views)
     gts = [torch.from_numpy(syn.make_gt_image(W, H, seed=1 + k)).pin_memory() for k in range(a.views)]
-    tr = pipeline.Trainer(scene, cams, gts, dev, 0, 1)
+    tr = pipeline.Trainer(scene, cams, gts, dev, rank, world)
     for _ in range(5):
         tr.step(resident=not a.e2e)
     torch.cuda.synchronize()
@@ -64,10 +71,14 @@ def main():
         for e in step:
             lines.append(f"  {e.time_range.start - t_begin:9.1f} +{e.time_range.end - e.time_range.start:8.1f}  {e.name[:90]}")
     out = "\n".join(lines)
-    print(out)
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"gap_profile_{a.views}v{'_e2e' if a.e2e else ''}.txt"), "w") as f:
-        f.write(out + "\n")
+    if rank == 0:
+        print(out)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"gap_profile_{world}gpu_{a.views}v{'_e2e' if a.e2e else ''}.txt"), "w") as f:
+            f.write(out + "\n")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
