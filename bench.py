@@ -358,20 +358,23 @@ def run_ours(args):
         for name, nb in (("strong_1view", 1), (f"views_{world // 2}", world // 2)):
             if nb < 1 or nb == B or (nb > 1 and name == "strong_1view"):
                 continue
-            tr2 = build_trainer(args, cfg, nb, dev, rank, world)
-            for _ in range(warmup):
-                tr2.step(resident=True)
-            m2, _, _ = timed_steps(tr2, max(5, steps // 2), True, barrier_sync)
-            ms2v = max_over_ranks(m2) / max(5, steps // 2)
-            i2 = tr2.last_info()
-            t2 = torch.tensor([i2["R"], i2["Vp"]], dtype=torch.float64, device=dev)
-            dist.all_reduce(t2)
-            extra[name] = {"views_per_step": nb, "ms_per_step": ms2v, "gaussians_per_s": N * nb / (ms2v * 1e-3),
-                           "instances_R_job": int(t2[0]), "splats_rendered_job": int(t2[1]),
-                           "strips_per_view": [len(st.gpu_ids) for st in tr2._strategies],
-                           "division_rows_view0": list(tr2._strategies[0].division_pos),
-                           "division_moves": len(tr2.balance_log) - 1}
-            del tr2
+            try:   # diagnostics must not cost the headline its line
+                tr2 = build_trainer(args, cfg, nb, dev, rank, world)
+                for _ in range(warmup):
+                    tr2.step(resident=True)
+                m2, _, _ = timed_steps(tr2, max(5, steps // 2), True, barrier_sync)
+                ms2v = max_over_ranks(m2) / max(5, steps // 2)
+                i2 = tr2.last_info()
+                t2 = torch.tensor([i2["R"], i2["Vp"]], dtype=torch.float64, device=dev)
+                dist.all_reduce(t2)
+                extra[name] = {"views_per_step": nb, "ms_per_step": ms2v, "gaussians_per_s": N * nb / (ms2v * 1e-3),
+                               "instances_R_job": int(t2[0]), "splats_rendered_job": int(t2[1]),
+                               "strips_per_view": [len(st.gpu_ids) for st in tr2._strategies],
+                               "division_rows_view0": list(tr2._strategies[0].division_pos),
+                               "division_moves": len(tr2.balance_log) - 1, "feedback_lag": tr2.feedback_lag}
+                del tr2
+            except Exception as e:   # noqa: BLE001
+                extra[name] = {"error": repr(e)[:300]}
             torch.cuda.empty_cache()
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -768,10 +768,37 @@ GS_D int xr_local_rank(uint32_t h, int j, int warp, int lane, int32_t (*s_wcnt)[
     return r;
 }
 
+// Destination rows computed ON THE DEVICE from the all-gathered counts cnt[i][k][j] (source, camera, destination), so that the
+// pack kernel can be enqueued before the host has read the counts (exchange.direct_rows is the host restatement):
+//   row0[j*B+k] = sum_{k' < k} sum_i cnt[i][k'][j]  +  sum_{i < me} cnt[i][k][j];   row0[W*B] = 1 if some rank would receive
+// more than `cap` rows (then the pack writes nothing and every rank -- same counts, same decision -- takes the fallback).
+__global__ void k_xr_rows(int W, int B, int me, const int32_t *__restrict__ cnt, long long cap, int32_t *__restrict__ row0) {
+    const int c = threadIdx.x;
+    if (c < W * B) {
+        const int j = c / B, k = c % B;
+        long long r = 0;
+        for (int kk = 0; kk < k; kk++)
+            for (int i = 0; i < W; i++) r += cnt[((size_t)i * B + kk) * W + j];
+        for (int i = 0; i < me; i++) r += cnt[((size_t)i * B + k) * W + j];
+        row0[c] = (int32_t)r;
+    }
+    if (c == 0) {
+        int over = 0;
+        for (int j = 0; j < W; j++) {
+            long long t = 0;
+            for (int i = 0; i < W; i++)
+                for (int k = 0; k < B; k++) t += cnt[((size_t)i * B + k) * W + j];
+            if (t > cap) over = 1;
+        }
+        row0[W * B] = over;
+    }
+}
+
 __global__ void __launch_bounds__(DT_THREADS)
-k_xr_pack(XrGeom g, XIn in, const int32_t *__restrict__ blkbase, XrPeers peers) {
+k_xr_pack(XrGeom g, XIn in, const int32_t *__restrict__ blkbase, XrPeers peers, const int32_t *__restrict__ row0_dev) {
     __shared__ int32_t s_wcnt[DT_THREADS / 32][XW];
     __shared__ float s_rgb[DT_THREADS / 32][96];
+    if (row0_dev != nullptr && row0_dev[g.Wr * g.B] != 0) return;   // over capacity: nothing is written (uniform)
     const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool valid = i < g.P;
@@ -807,7 +834,8 @@ k_xr_pack(XrGeom g, XIn in, const int32_t *__restrict__ blkbase, XrPeers peers) 
         for (int w = 0; w < warp; w++) lr += s_wcnt[w][j];
         const bool hit = (h >> j) & 1u;
         const size_t col = (size_t)j * g.B + k;
-        const long long row = (long long)peers.row0[col] + (blkbase[col * gridDim.x + blockIdx.x] - blkbase[col * gridDim.x]) + lr;
+        const long long row = (long long)(row0_dev ? row0_dev[col] : peers.row0[col]) +
+                              (blkbase[col * gridDim.x + blockIdx.x] - blkbase[col * gridDim.x]) + lr;
         float *b = reinterpret_cast<float *>(peers.base[j]);
         if (hit) {
             *reinterpret_cast<float2 *>(b + 2 * row) = m;
@@ -941,7 +969,38 @@ extern "C" int gs_xr_pack(int B, int P, int W, int image_height, int image_width
     XIn in;
     fill_in(in, B, means2D_ptrs_host, rgb_ptrs_host, conic_opacity_ptrs_host, radii_ptrs_host, depths_ptrs_host);
     GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
-    k_xr_pack<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers);
+    k_xr_pack<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers, nullptr);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+// gs_xr_pack with the destination rows computed on the device: counts_all_dev = the all-gathered counts (W*B*W int32,
+// [source i][camera k][destination j], as all_gather_into_tensor of every rank's (B,W) table leaves them), me = this rank,
+// row0_dev = (W*B + 1) int32 scratch that receives the rows and the over-capacity flag.  The caller needs no host copy of
+// the counts to launch it: the launch goes out right behind the all-gather and the host reads the counts while it runs.
+extern "C" int gs_xr_pack_dev(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                              const void *const *rgb_ptrs_host, const void *const *conic_opacity_ptrs_host,
+                              const void *const *radii_ptrs_host, const void *const *depths_ptrs_host,
+                              const int32_t *row_lo_host, const int32_t *row_hi_host, const int32_t *blkbase,
+                              void *const *peer_recv_ptrs_host, const int32_t *counts_all_dev, int me, int32_t *row0_dev,
+                              long long cap_rows, void *stream) {
+    XrGeom g;
+    int rc = xr_geom(g, B, P, W, image_height, image_width, means2D_ptrs_host, radii_ptrs_host, row_lo_host, row_hi_host);
+    if (rc != GS_OK) return rc;
+    GS_REQUIRE(counts_all_dev && row0_dev && me >= 0 && me < W, "device counts / row table / rank");
+    GS_REQUIRE(W * B <= 256, "W * B <= 256");
+    XrPeers peers;
+    int32_t zeros[XW * XB] = {0};
+    rc = xr_peers(peers, B, W, peer_recv_ptrs_host, zeros, cap_rows);
+    if (rc != GS_OK) return rc;
+    k_xr_rows<<<1, 256, 0, (cudaStream_t)stream>>>(W, B, me, counts_all_dev, cap_rows, row0_dev);
+    GS_LAUNCH_CHECK();
+    if (P == 0) return GS_OK;
+    GS_REQUIRE(rgb_ptrs_host && conic_opacity_ptrs_host && depths_ptrs_host && blkbase, "null pointer");
+    XIn in;
+    fill_in(in, B, means2D_ptrs_host, rgb_ptrs_host, conic_opacity_ptrs_host, radii_ptrs_host, depths_ptrs_host);
+    GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
+    k_xr_pack<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers, row0_dev);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

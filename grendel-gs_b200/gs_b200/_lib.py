@@ -81,6 +81,7 @@ SIGNATURES = {
     "gs_xr_temp_bytes": (_sz, [_i, _i, _i]),
     "gs_xr_count": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gs_xr_pack": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
+    "gs_xr_pack_dev": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, C.c_longlong, _vp]),
     "gs_xr_pull_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _vp, _vp, _vp, _vp]),
     "gs_sparse_grad_mask": (_i, [_i, _vp, _vp, _vp]),
     "gs_sparse_grad_pack": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),

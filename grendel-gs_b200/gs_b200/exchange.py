@@ -26,6 +26,9 @@ MAX_CAMERAS, MAX_RANKS, MAX_SEGMENTS = 16, 16, 128   # XB, XW, XSEG of csrc/dist
 # peer path (pack rows -> unpack), kept for A/B (GS_B200_EXCHANGE_MODE=rows)
 import os as _os
 MODE = _os.environ.get("GS_B200_EXCHANGE_MODE", "direct")
+# destination rows of the direct pack computed on the device, counts read on a side stream (no dry main stream at the
+# exchange's host sync); GS_B200_XR_DEVROWS=0: the host computes the rows before the pack is launched
+DEVICE_ROWS = _os.environ.get("GS_B200_XR_DEVROWS", "0") == "1"
 TRACE = None   # diagnostics: callable(name) that synchronises and charges the time since the last mark (pipeline._mark)
 
 
@@ -416,6 +419,27 @@ class _ExchangeSplatsDirect(torch.autograd.Function):
         return None, d_m2, d_rgb, d_co
 
 
+_SIDE = {}
+
+
+def _read_counts_on_side_stream(dev_tensor, ready_event, shape):
+    """Host copy of a small device tensor WITHOUT synchronising the current stream: a side stream waits for `ready_event`
+    (recorded right behind the producer), copies into pinned memory and only that copy is waited for."""
+    dev = dev_tensor.device
+    key = (dev, dev_tensor.numel(), dev_tensor.dtype)
+    if key not in _SIDE:
+        _SIDE[key] = (torch.cuda.Stream(device=dev), torch.empty((dev_tensor.numel(),), dtype=dev_tensor.dtype).pin_memory())
+    side, pinned = _SIDE[key]
+    side.wait_event(ready_event)
+    with torch.cuda.stream(side):
+        pinned.copy_(dev_tensor, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(side)
+    dev_tensor.record_stream(side)
+    done.synchronize()
+    return pinned.numpy().reshape(shape).copy()
+
+
 def open_peer_buffers(world, me, cap_rows, device, group=None):
     """PeerBuffers if every rank of the group could allocate, export and map them, else None on ALL ranks (the
     exchange then uses all_to_all_single).  Collective."""
@@ -485,16 +509,35 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
                      _slab_ptrs(radii, B), _slab_ptrs(depths, B), lo_c, hi_c, blkbase.data_ptr(),
                      (C.c_void_p * world)(*peer.recv))
         cap, stream = C.c_longlong(peer.cap_rows), ops._stream()
-        cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]
-        _t("x2 gather counts")
+        # The sizes are all-gathered ON THE DEVICE and the pack kernel derives its destination rows from them there
+        # (k_xr_rows), so pack + barrier are enqueued before the host knows the counts; the host copy of the counts -- needed
+        # for the tensor shapes of the render -- is read on a side stream meanwhile.  The main stream does not run dry at the
+        # exchange's host sync (the reference blocks on the sizes before its all-to-all, gaussian_renderer/__init__.py:609-628).
+        if DEVICE_ROWS:
+            flat = counts.t().contiguous().reshape(-1)                    # [camera k][destination j]
+            allc = torch.empty((world * flat.numel(),), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(allc, flat, group=group)          # cnt[i][k][j]
+            ev_counts = torch.cuda.Event()
+            ev_counts.record()
+            row0_dev = torch.empty((world * B + 1,), dtype=torch.int32, device=dev)
+            _lib.call("gs_xr_pack_dev", *pack_args, allc.data_ptr(), me, row0_dev.data_ptr(), cap, stream)
+            _t("x3 pack")
+            peer.barrier()
+            _t("x4 all_to_all")
+            cnt = _read_counts_on_side_stream(allc, ev_counts, (world, B, world))
+            _t("x2 gather counts")
+        else:
+            cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]
+            _t("x2 gather counts")
         c64 = np.asarray(cnt, dtype=np.int64)
         if int(c64.sum(axis=(0, 1)).max()) <= peer.cap_rows:
             row0, view_start = direct_rows(c64, me)       # decided from the all-gathered counts: identical on all ranks
             row0_c = _i32(row0)
-            _lib.call("gs_xr_pack", *pack_args, row0_c, cap, stream)
-            _t("x3 pack")
-            peer.barrier()
-            _t("x4 all_to_all")
+            if not DEVICE_ROWS:
+                _lib.call("gs_xr_pack", *pack_args, row0_c, cap, stream)
+                _t("x3 pack")
+                peer.barrier()
+                _t("x4 all_to_all")
             state = dict(group=group, radii=radii, depths=depths, m2d=m2d, blkbase=blkbase, B=B, P=P, W=world, H=H,
                          Wimg=Wimg, lo=lo_c, hi=hi_c, row0=row0_c, view_start=view_start, peer=peer, cnt=cnt, me=me,
                          keep=(rgb_c, co_c))

@@ -162,7 +162,7 @@ class Trainer:
         self.load_balance, self.heuristic_decay = load_balance, heuristic_decay
         if feedback_lag is None:
             import os as _os
-            feedback_lag = int(_os.environ.get("GS_B200_FEEDBACK_LAG", "1"))
+            feedback_lag = int(_os.environ.get("GS_B200_FEEDBACK_LAG", "0"))
         self.feedback_lag = max(0, int(feedback_lag))
         self._pending_feedback = []
         self._fb_group = None

@@ -368,6 +368,16 @@ GS_API int gs_xchg_pack_grad_p2p(int nseg, const int32_t *seg_recv_start_host, c
                                  const void *const *d_conic_opacity_ptrs_host, void *const *seg_dst_ptrs_host,
                                  void *stream);
 
+/* gs_xr_pack with the destination rows computed on the device from the all-gathered counts (counts_all_dev: W*B*W int32,
+ * [source][camera][destination]; row0_dev: W*B + 1 int32 scratch = rows + over-capacity flag): enqueued right behind the
+ * all-gather of gaussian_renderer/__init__.py:609-628's sizes, before the host has read them -- the stream does not run
+ * dry at the exchange's host sync.  Over capacity nothing is written and every rank takes the all_to_all_single path. */
+GS_API int gs_xr_pack_dev(int B, int P, int W, int image_height, int image_width, const void *const *means2D_ptrs_host,
+                          const void *const *rgb_ptrs_host, const void *const *conic_opacity_ptrs_host,
+                          const void *const *radii_ptrs_host, const void *const *depths_ptrs_host,
+                          const int32_t *row_lo_host, const int32_t *row_hi_host, const int32_t *blkbase,
+                          void *const *peer_recv_ptrs_host, const int32_t *counts_all_dev, int me, int32_t *row0_dev,
+                          long long cap_rows, void *stream);
 /* ---- direct-placement exchange (csrc/distribute.cu, "xr"): same collective, same row order, but nothing is staged --
  * gs_xr_count: per (destination rank j, camera k, block of 256 splats) hit counts + their exclusive scan + the (j,k)
  * totals (the counts every rank all-gathers, gaussian_renderer/__init__.py:574-588).
