@@ -28,7 +28,7 @@ import os as _os
 MODE = _os.environ.get("GS_B200_EXCHANGE_MODE", "direct")
 # destination rows of the direct pack computed on the device, counts read on a side stream (no dry main stream at the
 # exchange's host sync); GS_B200_XR_DEVROWS=0: the host computes the rows before the pack is launched
-DEVICE_ROWS = _os.environ.get("GS_B200_XR_DEVROWS", "0") == "1"
+DEVICE_ROWS = _os.environ.get("GS_B200_XR_DEVROWS", "1") == "1"
 TRACE = None   # diagnostics: callable(name) that synchronises and charges the time since the last mark (pipeline._mark)
 
 

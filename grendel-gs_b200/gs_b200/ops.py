@@ -310,7 +310,7 @@ class _RenderGaussians(torch.autograd.Function):
         _lib.call("gs_render_count_launch", 1, None, P, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
                   depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(),
                   rec.data_ptr(), temp.data_ptr(), tb, C.byref(ticket), s)
-        key = (1, P, H, W, needs_grad)
+        key = (1, H, W, needs_grad)          # not P: the splat count of a strip varies from step to step, R follows it smoothly
         pre = _instance_buffers_before_sync(key, T, dev, needs_grad)    # host work while the count / sort / scan run
         _lib.call("gs_render_count_read", ticket, C.byref(R), s)   # the operator's one host sync
         R = int(R.value)
@@ -432,7 +432,7 @@ class _RenderGaussiansBatched(torch.autograd.Function):
         _lib.call("gs_render_count_launch", B, vs, P, H, W, means2D.data_ptr(), conic_opacity.data_ptr(), rgb.data_ptr(),
                   depths.data_ptr(), radii.data_ptr(), cl.data_ptr(), order.data_ptr(), offsets.data_ptr(),
                   rec.data_ptr(), temp.data_ptr(), tb, C.byref(ticket), s)
-        key = (B, P, H, W, needs_grad)
+        key = (B, H, W, needs_grad)
         pre = _instance_buffers_before_sync(key, B * T, dev, needs_grad)   # host work while the count / sort / scan run
         _lib.call("gs_render_count_read", ticket, C.byref(R), s)    # the operator's one host sync
         R = int(R.value)

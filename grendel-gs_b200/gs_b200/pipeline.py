@@ -162,7 +162,7 @@ class Trainer:
         self.load_balance, self.heuristic_decay = load_balance, heuristic_decay
         if feedback_lag is None:
             import os as _os
-            feedback_lag = int(_os.environ.get("GS_B200_FEEDBACK_LAG", "0"))
+            feedback_lag = int(_os.environ.get("GS_B200_FEEDBACK_LAG", "1"))
         self.feedback_lag = max(0, int(feedback_lag))
         self._pending_feedback = []
         self._fb_group = None
@@ -202,11 +202,26 @@ class Trainer:
             if key not in self._strip_cache:
                 self._strip_cache[key] = self.gts_dev[k][:, y0:y1, :].contiguous()
             return self._strip_cache[key]
-        if key not in self._strip_cache:  # pinned, contiguous staging copy of the strip rows
-            self._strip_cache[key] = self.gts_host[k][:, y0:y1, :].contiguous().pin_memory()
-        h = self._strip_cache[key]
-        self._h2d += h.numel()
-        return h.to(self.device, non_blocking=True)
+        return self._strip_h2d(k, y0, y1)
+
+    def _strip_h2d(self, k, y0, y1):
+        """Rows [y0, y1) of the pinned (3,H,W) uint8 ground truth -> a (3, rows, W) device strip: the rows of one channel
+        are contiguous in the pinned image, so the strip is three asynchronous copies straight out of it -- no staging
+        copy, and nothing to re-pin when the load balancer moves the strip boundaries (a pinned staging strip per
+        division cost several ms of cudaHostAlloc every time the strips of a 4K view moved)."""
+        host = self.gts_host[k]
+        if not host.is_pinned():
+            key = (k, y0, y1, False)
+            if key not in self._strip_cache:
+                self._strip_cache[key] = host[:, y0:y1, :].contiguous().pin_memory()
+            h = self._strip_cache[key]
+            self._h2d += h.numel()
+            return h.to(self.device, non_blocking=True)
+        d = torch.empty((3, y1 - y0, self.W), dtype=torch.uint8, device=self.device)
+        for c in range(3):
+            d[c].copy_(host[c, y0:y1, :], non_blocking=True)
+        self._h2d += d.numel()
+        return d
 
     def _mark(self, name):
         """GS_B200_TRACE=1: synchronise and accumulate wall-clock per phase (diagnostics only)."""
@@ -269,13 +284,8 @@ class Trainer:
                 rows = st.local_pixel_rows(self.H)
                 if rows is None:
                     continue
-                key = (k, rows[0], rows[1], False)
-                if key not in self._strip_cache:  # pinned, contiguous staging copy of the strip rows
-                    self._strip_cache[key] = self.gts_host[k][:, rows[0]:rows[1], :].contiguous().pin_memory()
-                h = self._strip_cache[key]
-                self._h2d += h.numel()
                 with torch.cuda.stream(self._copy_stream):
-                    d = h.to(self.device, non_blocking=True)
+                    d = self._strip_h2d(k, rows[0], rows[1])
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)
                 gt_ready[k] = (d, ev)

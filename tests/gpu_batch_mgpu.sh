@@ -6,7 +6,7 @@ N=${1:-2}; TAG=${2:-r2x}
 OUT=gpurun_out
 mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 400 $TR --master-port 29511 tests/mgpu_parity.py > $OUT/${TAG}_mgpu_parity_${N}gpu.log 2>&1; echo "parity rc=$?"
+timeout ${PARITY_TIMEOUT:-300} $TR --master-port 29511 tests/mgpu_parity.py > $OUT/${TAG}_mgpu_parity_${N}gpu.log 2>&1; echo "parity rc=$?"
 tail -4 $OUT/${TAG}_mgpu_parity_${N}gpu.log
 show() { python - "$1" <<'PY'
 import json, sys
