@@ -101,13 +101,36 @@ def all_to_all_single(out, inp, out_splits, in_splits, group=None):
         outs[p].copy_(b)
 
 
+# Timing feedback rides on the exchange: the render times a rank wants to share (a few floats, finish_strategy_final's
+# all-gather of utils/general_utils.py:249-269) are all-gathered right behind the sizes and read back with them -- no
+# collective of their own on the critical path, no extra host sync.  The caller (pipeline.Trainer) sets PIGGYBACK_IN to a
+# list of floats before the exchange (None on steps without feedback: the same on every rank) and reads PIGGYBACK_OUT, a
+# (W, len) array, afterwards.
+PIGGYBACK_IN = None
+PIGGYBACK_OUT = None
+
+
+def _piggyback_gather(dev, world, group):
+    """Enqueue the all-gather of PIGGYBACK_IN (if any) on the current stream -> device tensor (W * E) or None."""
+    if PIGGYBACK_IN is None:
+        return None
+    mine = torch.tensor([float(v) for v in PIGGYBACK_IN], dtype=torch.float32, device=dev)
+    allp = torch.empty((world * mine.numel(),), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(allp, mine, group=group)
+    return allp
+
+
 def gather_counts(local_counts, group=None):
     """(B, W) int32 device tensor -> (W, B, W) integer array cnt[i][k][j]; the step's one host sync."""
+    global PIGGYBACK_OUT
     W = dist.get_world_size(group)
     flat = local_counts.contiguous().reshape(-1)
     allc = torch.empty((W * flat.numel(),), dtype=flat.dtype, device=flat.device)
     dist.all_gather_into_tensor(allc, flat, group=group)
-    return allc.reshape((W,) + tuple(local_counts.shape)).cpu().numpy()
+    allp = _piggyback_gather(flat.device, W, group) if flat.is_cuda else None
+    out = allc.reshape((W,) + tuple(local_counts.shape)).cpu().numpy()
+    PIGGYBACK_OUT = None if allp is None else allp.reshape(W, -1).cpu().numpy()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -517,6 +540,7 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
             flat = counts.t().contiguous().reshape(-1)                    # [camera k][destination j]
             allc = torch.empty((world * flat.numel(),), dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(allc, flat, group=group)          # cnt[i][k][j]
+            allp = _piggyback_gather(dev, world, group)
             ev_counts = torch.cuda.Event()
             ev_counts.record()
             row0_dev = torch.empty((world * B + 1,), dtype=torch.int32, device=dev)
@@ -524,7 +548,9 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
             _t("x3 pack")
             peer.barrier()
             _t("x4 all_to_all")
+            global PIGGYBACK_OUT
             cnt = _read_counts_on_side_stream(allc, ev_counts, (world, B, world))
+            PIGGYBACK_OUT = None if allp is None else _read_counts_on_side_stream(allp, ev_counts, (world, -1))
             _t("x2 gather counts")
         else:
             cnt = gather_counts(counts.t().contiguous(), group)          # cnt[i][k][j]

@@ -123,11 +123,11 @@ class Trainer:
         distributed_dataset_storage: only rank 0 holds the ground-truth images (gts_pinned may be None elsewhere); the
         strips of a resident=False step are scattered from rank 0's GPU (loss_distribution.py:2395-2533, gt_scatter.py)
         instead of being read from every rank's own host copy.
-        feedback_lag: the timing feedback of step k uses the render times of step k - feedback_lag.  0 = the reference's
-        sequencing (finish_strategy_final right after the step: the host waits for the device at the end of every step and
-        cannot enqueue ahead); 1 (default, GS_B200_FEEDBACK_LAG) = the times of the PREVIOUS step, whose events have
-        completed, exchanged by a host-side (gloo) all-gather that never touches the CUDA streams -- the strips move one
-        step later and the device never waits for the host."""
+        feedback_lag: 0 = the reference's sequencing (finish_strategy_final right after the step: the render times are
+        read, all-gathered and applied before the next step starts, so the host waits for the device at the end of every
+        step and cannot enqueue ahead).  > 0 (default 2, GS_B200_FEEDBACK_LAG) = the times of the step `feedback_lag`
+        steps back, whose events have long completed, ride on the NEXT exchange's size all-gather (exchange.PIGGYBACK_IN):
+        no collective of their own, no host sync; the strips move the same way, `feedback_lag` steps later."""
         from . import exchange as _ex
         self._ex = _ex
         # splat / gradient rows travel by direct NVLink stores from the pack kernels (exchange.PeerBuffers) instead of
@@ -162,18 +162,10 @@ class Trainer:
         self.load_balance, self.heuristic_decay = load_balance, heuristic_decay
         if feedback_lag is None:
             import os as _os
-            feedback_lag = int(_os.environ.get("GS_B200_FEEDBACK_LAG", "1"))
+            feedback_lag = int(_os.environ.get("GS_B200_FEEDBACK_LAG", "2"))
         self.feedback_lag = max(0, int(feedback_lag))
-        self._pending_feedback = []
-        self._fb_group = None
-        if world > 1 and load_balance and self.feedback_lag > 0:
-            import torch.distributed as _dist
-            if _dist.get_backend(group) != "gloo":   # times travel host to host: no CUDA stream is synchronised for them
-                import os as _os
-                if _os.environ.get("MASTER_ADDR", "") in ("127.0.0.1", "localhost") and "GLOO_SOCKET_IFNAME" not in _os.environ:
-                    _os.environ["GLOO_SOCKET_IFNAME"] = "lo"   # single-node rendezvous: the hostname may not resolve
-                ranks = list(range(world)) if group is None else _dist.get_process_group_ranks(group)
-                self._fb_group = _dist.new_group(ranks=ranks, backend="gloo")
+        self._pending_feedback = []     # steps whose render times have not been fed back yet, oldest first
+        self._sent_feedback = None      # the step whose times ride on the exchange of the current step
         self.iteration = 0
         self.balance_log = []      # (iteration, division rows of camera 0) whenever the division moved
         self.dcams = [DeviceCamera(c, device) for c in cams]
@@ -327,12 +319,14 @@ class Trainer:
             batched = tuple(torch.stack([s[q] for s in screen]) for q in range(5))
         cat = view_start = None
         if self.world > 1:
+            self._feedback_before_exchange()
             if use_batched:
                 cat, view_start, cnt = self._ex.exchange_cat(*batched, strategies, settings, self.world, self.rank,
                                                              self.group, self._peer)
             else:
                 redistributed, cnt = self._ex.exchange(*batched, strategies, settings, self.world, self.rank, self.group,
                                                        self._peer)
+            self._feedback_after_exchange()
         elif use_batched:   # (B,P,.) stacked IS the concatenation: camera k = rows [k P, (k+1) P)
             Pn = batched[0].shape[1]
             cat = (batched[0].reshape(-1, 2), batched[1].reshape(-1, 3), batched[2].reshape(-1, 4),
@@ -430,26 +424,10 @@ class Trainer:
         torch.cuda.current_stream().synchronize()
         return float(self._loss_host[0])
 
-    def _feed_back_times(self, strategies, collectors):
-        """finish_strategy_final (workload_division.py:944-998) + the time all-gather (utils/general_utils.py:249-269):
-        every rank contributes the render time of each camera it rendered a strip of; the per-row cost heuristic is
-        rebuilt from them and the NEXT step's strips move.  Only where the reference's gate enables it (more than one
-        rank, and not when whole <= 1080p images can be handed out)."""
-        import torch.distributed as dist
+    def _times_of(self, strategies, collectors, n_renders):
+        """This rank's gpu_camera_running_time row for one step: the render time of each camera it rendered a strip of."""
         from .division import running_time_of
         B = len(strategies)
-        if not (self.load_balance and self.world > 1 and
-                heuristics_update_enabled(self.iteration, self.world, B, self.H, self.W)):
-            self._pending_feedback.clear()
-            return
-        iteration, n_renders = self.iteration, self._n_renders
-        if self.feedback_lag > 0:
-            # this step's events are still in flight: queue it, and feed back the step that is feedback_lag steps old
-            self._pending_feedback.append((strategies, collectors, iteration, n_renders))
-            if len(self._pending_feedback) <= self.feedback_lag:
-                return
-            strategies, collectors, iteration, n_renders = self._pending_feedback.pop(0)
-            B = len(strategies)
         mine = [-1.0] * B
         rows = [(st.local_rows()[1] - st.local_rows()[0]) if st.local_rows() is not None else 0 for st in strategies]
         if n_renders == 1 and sum(1 for r in rows if r) > 1:
@@ -464,17 +442,47 @@ class Trainer:
                 if r:
                     c = collectors[k] if "forward_render_time" in collectors[k] else collectors[0]
                     mine[k] = running_time_of(c)
-        if self.feedback_lag > 0 and (self._fb_group is not None or dist.get_backend(self.group) == "gloo"):
-            loc = torch.tensor(mine, dtype=torch.float32)          # host tensors over gloo
-            parts = [torch.empty_like(loc) for _ in range(self.world)]
-            dist.all_gather(parts, loc, group=self._fb_group if self._fb_group is not None else self.group)
-            times = torch.stack(parts).tolist()
-        else:
-            loc = torch.tensor(mine, dtype=torch.float32, device=self.device)
-            allt = torch.empty((self.world * B,), dtype=torch.float32, device=self.device)
-            dist.all_gather_into_tensor(allt, loc, group=self.group)
-            times = allt.reshape(self.world, B).cpu().tolist()       # gpu_camera_running_time[gpu][camera]
-        finish_strategy(self.history, strategies, times, iteration, self.world, self.H, self.W, self.heuristic_decay)
+        return mine
+
+    def _feedback_before_exchange(self):
+        """feedback_lag > 0: hand the render times of the step `feedback_lag` steps back (its events have completed: the
+        host is never more than one step ahead of the device) to the exchange, which all-gathers them behind the sizes."""
+        self._ex.PIGGYBACK_IN, self._sent_feedback = None, None
+        if self.feedback_lag > 0 and len(self._pending_feedback) >= self.feedback_lag:
+            entry = self._pending_feedback.pop(0)
+            self._ex.PIGGYBACK_IN = self._times_of(entry[0], entry[1], entry[3])
+            self._sent_feedback = entry
+
+    def _feedback_after_exchange(self):
+        if self._sent_feedback is None:
+            return
+        strategies, _collectors, iteration, _n = self._sent_feedback
+        times = self._ex.PIGGYBACK_OUT
+        self._ex.PIGGYBACK_IN, self._sent_feedback = None, None
+        if times is not None:
+            finish_strategy(self.history, strategies, times.tolist(), iteration, self.world, self.H, self.W,
+                            self.heuristic_decay)
+
+    def _feed_back_times(self, strategies, collectors):
+        """finish_strategy_final (workload_division.py:944-998) + the time all-gather (utils/general_utils.py:249-269):
+        every rank contributes the render time of each camera it rendered a strip of; the per-row cost heuristic is
+        rebuilt from them and the strips of a later step move.  Only where the reference's gate enables it (more than
+        one rank, and not when whole <= 1080p images can be handed out)."""
+        import torch.distributed as dist
+        B = len(strategies)
+        if not (self.load_balance and self.world > 1 and
+                heuristics_update_enabled(self.iteration, self.world, B, self.H, self.W)):
+            self._pending_feedback.clear()
+            return
+        if self.feedback_lag > 0:   # fed back later, on the size all-gather of a coming exchange (_feedback_before_exchange)
+            self._pending_feedback.append((strategies, collectors, self.iteration, self._n_renders))
+            return
+        mine = self._times_of(strategies, collectors, self._n_renders)
+        loc = torch.tensor(mine, dtype=torch.float32, device=self.device)
+        allt = torch.empty((self.world * B,), dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(allt, loc, group=self.group)
+        times = allt.reshape(self.world, B).cpu().tolist()       # gpu_camera_running_time[gpu][camera]
+        finish_strategy(self.history, strategies, times, self.iteration, self.world, self.H, self.W, self.heuristic_decay)
 
     GROUP_OF = {"xyz": "_xyz", "f_dc": "_features_dc", "f_rest": "_features_rest", "opacity": "_opacity",
                 "scaling": "_scaling", "rotation": "_rotation"}

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--views", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--e2e", action="store_true")
+    ap.add_argument("--cprofile", action="store_true", help="also print the host-side hot spots of 30 steps (cProfile)")
     a = ap.parse_args()
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -44,6 +45,20 @@ def main():
     t_host = (time.perf_counter() - t0) / 20     # host time to ENQUEUE a step (no sync inside the loop except R)
     torch.cuda.synchronize()
     t_all = (time.perf_counter() - t0) / 20
+    if a.cprofile and rank == 0:
+        import cProfile, io, pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(30):
+            tr.step(resident=not a.e2e)
+        pr.disable()
+        torch.cuda.synchronize()
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(35)
+        print("host hot spots over 30 steps (cProfile, tottime):\n" + buf.getvalue()[:6000])
+    elif a.cprofile:
+        for _ in range(30):
+            tr.step(resident=not a.e2e)
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         for _ in range(a.steps):
             tr.step(resident=not a.e2e)

@@ -23,7 +23,7 @@ if [ -n "$NCU" ]; then
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_blend.log 2>&1; echo "ncu rc=$?"
 fi
 if [ -n "$GAPS" ]; then
-  timeout 300 python tests/gap_profile.py > $OUT/${TAG}_gaps.log 2>&1; echo "gaps rc=$?"; head -12 $OUT/${TAG}_gaps.log
+  timeout 300 python tests/gap_profile.py --cprofile > $OUT/${TAG}_gaps.log 2>&1; echo "gaps rc=$?"; head -12 $OUT/${TAG}_gaps.log
 fi
 if [ -n "$SANITY" ]; then
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1"

@@ -21,15 +21,15 @@ PY
 timeout 600 $TR --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_${N}gpu.json \
     2> $OUT/${TAG}_bench_${N}gpu.err; echo "bench rc=$?"; show $OUT/${TAG}_bench_${N}gpu.json; tail -2 $OUT/${TAG}_bench_${N}gpu.err
 if [ -n "$GAPS" ]; then
-  timeout 300 $TR --master-port 29515 tests/gap_profile.py --views $N > $OUT/${TAG}_gaps_${N}gpu.log 2>&1; echo "gaps rc=$?"
+  timeout 300 $TR --master-port 29515 tests/gap_profile.py --views $N --cprofile > $OUT/${TAG}_gaps_${N}gpu.log 2>&1; echo "gaps rc=$?"
   head -30 $OUT/${TAG}_gaps_${N}gpu.log | cut -c1-200
 fi
-if [ "$N" = 4 ]; then
+if [ "$N" = 4 ] && [ -z "$SKIP_CFG" ]; then
   timeout 600 $TR --master-port 29513 bench.py --gpus 4 --workload c3 --steps 20 --warmup 5 --no-cpu-baseline --time-optimizer \
       > $OUT/${TAG}_bench_c3_4gpu.json 2> $OUT/${TAG}_bench_c3_4gpu.err; echo "c3 rc=$?"; show $OUT/${TAG}_bench_c3_4gpu.json
   tail -2 $OUT/${TAG}_bench_c3_4gpu.err
 fi
-if [ "$N" = 8 ]; then
+if [ "$N" = 8 ] && [ -z "$SKIP_CFG" ]; then
   timeout 900 $TR --master-port 29513 bench.py --gpus 8 --workload c4 --steps 10 --warmup 3 --no-cpu-baseline --no-extra \
       --time-optimizer > $OUT/${TAG}_bench_c4_8gpu.json 2> $OUT/${TAG}_bench_c4_8gpu.err; echo "c4 rc=$?"
   show $OUT/${TAG}_bench_c4_8gpu.json; tail -2 $OUT/${TAG}_bench_c4_8gpu.err
