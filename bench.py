@@ -360,7 +360,7 @@ def run_ours(args):
                 continue
             try:   # diagnostics must not cost the headline its line
                 tr2 = build_trainer(args, cfg, nb, dev, rank, world)
-                for _ in range(warmup):
+                for _ in range(warmup + 5):   # moving strips: a few more steps until the allocator has seen every size
                     tr2.step(resident=True)
                 m2, _, _ = timed_steps(tr2, max(5, steps // 2), True, barrier_sync)
                 ms2v = max_over_ranks(m2) / max(5, steps // 2)

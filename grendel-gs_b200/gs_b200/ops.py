@@ -16,8 +16,13 @@ BLOCK_X, BLOCK_Y, ONE_DIM_BLOCK_SIZE = 16, 16, 256
 LAST_R_TOTAL = 0  # instances binned by the most recent render_gaussians calls (reset by the caller)
 
 
+# torch.cuda.current_stream() costs ~20 us of Python per call and every operator asks for it: a caller that runs a whole
+# step on one stream (pipeline.Trainer.step) pins the handle here for the duration of the step (None = ask torch)
+STEP_STREAM = None
+
+
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return STEP_STREAM if STEP_STREAM is not None else torch.cuda.current_stream().cuda_stream
 
 
 def _f32c(t, name):
@@ -239,7 +244,7 @@ class _InstanceBuffers:
     __slots__ = ("cap", "tiles", "ids", "sort_temp", "sb", "seg", "segb")
 
     def __init__(self, cap, num_tiles, dev, needs_grad):
-        self.cap = max(int(cap), 1)
+        self.cap = _q(cap)
         self.tiles = torch.empty((2, self.cap), dtype=torch.int32, device=dev)
         self.ids = torch.empty((2, self.cap), dtype=torch.int32, device=dev)
         self.sb = _lib.query("gs_render_sort_temp_bytes", self.cap)
@@ -262,10 +267,19 @@ def _instance_buffers_after_sync(key, pre, R, num_tiles, dev, needs_grad):
     return _InstanceBuffers(R, num_tiles, dev, needs_grad)
 
 
+def _q(n):
+    """Buffer sizes that follow a data-dependent count (received splats, instances) are rounded up to 1/16 steps of their
+    leading power of two: when the strips of a view move, the counts change a little every step, and exact sizes would
+    hand the caching allocator a new size -- eventually a cudaMalloc and a device synchronisation -- every few steps."""
+    n = max(int(n), 1)
+    q = 1 << max(10, n.bit_length() - 5)
+    return (n + q - 1) // q * q
+
+
 def _grad_block(P, dev):
     """dL/dmeans2D (P,2), dL/dconic_opacity (P,4), dL/drgb (P,3) as consecutive blocks of ONE allocation: the backward
     zeroes them with one memset instead of three (it accumulates into them with RED.ADD)."""
-    buf = torch.empty((9 * max(P, 1),), dtype=torch.float32, device=dev)   # conic first: its rows are read as float4
+    buf = torch.empty((9 * _q(P),), dtype=torch.float32, device=dev)   # conic first: its rows are read as float4
     return buf[4 * P:6 * P].view(P, 2), buf[:4 * P].view(P, 4), buf[6 * P:9 * P].view(P, 3)
 
 
@@ -294,10 +308,11 @@ class _RenderGaussians(torch.autograd.Function):
         s = _stream()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        offsets = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
-        order = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
-        rec = torch.empty((max(P, 1), 12), dtype=torch.float32, device=dev)
-        tb = _lib.query("gs_render_count_temp_bytes", P)
+        Pq = _q(P)
+        offsets = torch.empty((Pq,), dtype=torch.int32, device=dev)
+        order = torch.empty((Pq,), dtype=torch.int32, device=dev)
+        rec = torch.empty((Pq, 12), dtype=torch.float32, device=dev)
+        tb = _lib.query("gs_render_count_temp_bytes", Pq)
         temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
         image = torch.empty((3, H, W), dtype=torch.float32, device=dev)
@@ -416,10 +431,11 @@ class _RenderGaussiansBatched(torch.autograd.Function):
         vs = _i32_array(view_start)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        offsets = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
-        order = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
-        rec = torch.empty((max(P, 1), 12), dtype=torch.float32, device=dev)
-        tb = _lib.query("gs_render_count_temp_bytes", P)
+        Pq = _q(P)
+        offsets = torch.empty((Pq,), dtype=torch.int32, device=dev)
+        order = torch.empty((Pq,), dtype=torch.int32, device=dev)
+        rec = torch.empty((Pq, 12), dtype=torch.float32, device=dev)
+        tb = _lib.query("gs_render_count_temp_bytes", Pq)
         temp = torch.empty((tb,), dtype=torch.uint8, device=dev)
         ranges = torch.empty((B * T, 2), dtype=torch.int32, device=dev)
         image = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)

@@ -228,6 +228,13 @@ class Trainer:
     def step(self, resident=True):
         """One forward + loss + backward over the batch.  resident=False copies the GT strips from pinned host
         memory inside the step and reads the loss back (the end-to-end leg); returns the loss as a float then."""
+        ops.STEP_STREAM = torch.cuda.current_stream().cuda_stream   # every kernel of the step goes to this stream
+        try:
+            return self._step(resident)
+        finally:
+            ops.STEP_STREAM = None
+
+    def _step(self, resident):
         import os as _os, time as _time
         self._trace_on = _os.environ.get("GS_B200_TRACE") == "1"
         self._ex.TRACE = self._mark if self._trace_on else None

@@ -24,6 +24,11 @@ if [ -n "$GAPS" ]; then
   timeout 300 $TR --master-port 29515 tests/gap_profile.py --views $N --cprofile > $OUT/${TAG}_gaps_${N}gpu.log 2>&1; echo "gaps rc=$?"
   head -30 $OUT/${TAG}_gaps_${N}gpu.log | cut -c1-200
 fi
+if [ -n "$STRONG" ]; then
+  timeout 300 $TR --master-port 29516 tests/gap_profile.py --views 1 --cprofile > $OUT/${TAG}_gaps_strong_${N}gpu.log 2>&1; echo "strong gaps rc=$?"
+  grep -A28 "host hot spots" $OUT/${TAG}_gaps_strong_${N}gpu.log | cut -c1-160
+  grep -m3 "host enqueue\|last full step" $OUT/${TAG}_gaps_strong_${N}gpu.log
+fi
 if [ "$N" = 4 ] && [ -z "$SKIP_CFG" ]; then
   timeout 600 $TR --master-port 29513 bench.py --gpus 4 --workload c3 --steps 20 --warmup 5 --no-cpu-baseline --time-optimizer \
       > $OUT/${TAG}_bench_c3_4gpu.json 2> $OUT/${TAG}_bench_c3_4gpu.err; echo "c3 rc=$?"; show $OUT/${TAG}_bench_c3_4gpu.json
