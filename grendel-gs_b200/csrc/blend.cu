@@ -39,7 +39,9 @@
 #define BL_THREADS 256
 #define BL_WARPS (BL_THREADS / 32)
 #define BL_BLOCKS 16  // 4x4 pixel blocks per tile
+#ifndef FW_CHUNK
 #define FW_CHUNK 256
+#endif
 
 #define ALPHA_MIN (1.0f / 255.0f)
 #define ALPHA_MAX 0.99f
@@ -220,14 +222,14 @@ k_blend_fwd(int W, int H, int tiles_per_view, const float4 *__restrict__ rec, co
     for (int base = 0; base < total; base += FW_CHUNK) {
         if (__syncthreads_count(done) == BL_THREADS) break;
         const int cnt = min(FW_CHUNK, total - base);
-        if ((int)threadIdx.x < cnt) {
-            const uint32_t g = ids[range.x + base + threadIdx.x];
+        for (int i = threadIdx.x; i < cnt; i += BL_THREADS) {
+            const uint32_t g = ids[range.x + base + i];
             const float4 *r = rec + (size_t)3 * g;
             const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-            s_rec[threadIdx.x].a = a; s_rec[threadIdx.x].b = b; s_rec[threadIdx.x].c = c;
+            s_rec[i].a = a; s_rec[i].b = b; s_rec[i].c = c;
             const uint16_t m16 = (uint16_t)block_mask16(a, b, c.z, c.w, X0, Y0);
-            s_cull[threadIdx.x] = m16;
-            if (CKPT) seg.cull[range.x + base + threadIdx.x] = m16;
+            s_cull[i] = m16;
+            if (CKPT) seg.cull[range.x + base + i] = m16;
         }
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {

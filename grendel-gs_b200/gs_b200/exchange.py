@@ -108,6 +108,7 @@ def all_to_all_single(out, inp, out_splits, in_splits, group=None):
 # (W, len) array, afterwards.
 PIGGYBACK_IN = None
 PIGGYBACK_OUT = None
+_WARNED_OVER_CAPACITY = False
 
 
 def _piggyback_gather(dev, world, group):
@@ -570,6 +571,12 @@ def exchange_cat(means2D, rgb, conic_opacity, radii, depths, strategies, setting
             res = _ExchangeSplatsDirect.apply(state, means2D, rgb, conic_opacity)
             return res, view_start, cnt
         # does not fit the buffers this step: the row-staged path below (all_to_all_single) handles any size
+        global _WARNED_OVER_CAPACITY
+        if not _WARNED_OVER_CAPACITY and me == 0:
+            import warnings
+            warnings.warn(f"exchange: {int(c64.sum(axis=(0, 1)).max())} rows for one rank exceed the peer buffers "
+                          f"({peer.cap_rows} rows): this step goes through all_to_all_single (raise peer_cap_rows)")
+            _WARNED_OVER_CAPACITY = True
     n = max(B * P * world, 1)
     flags = torch.empty((n,), dtype=torch.uint8, device=dev)
     gpos = torch.empty((n,), dtype=torch.int32, device=dev)

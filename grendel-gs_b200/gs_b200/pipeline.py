@@ -143,6 +143,14 @@ class Trainer:
             # receive / send total.  1.25 x the scene per view, capped by what a step can produce.
             cap = int(peer_cap_rows) if peer_cap_rows else int(1.25 * n) + 65536
             self._peer = _ex.open_peer_buffers(world, rank, cap, device, group)
+        if world > 1:
+            # NCCL connects the point-to-point channels of all_to_all_single lazily, on first use: ~7 s on an 8-GPU box.  The
+            # exchange needs them only when a step exceeds the peer buffers (and the redistribution after densification
+            # always does): pay for the set-up here, not inside whichever training step happens to be the first.
+            import torch.distributed as _dist
+            if _dist.get_backend(group) == "nccl":
+                _w = torch.zeros((world,), dtype=torch.float32, device=device)
+                _dist.all_to_all_single(torch.empty_like(_w), _w, group=group)
         # bin + blend + loss of all B cameras in one pass (ops.render_gaussians_batched) instead of the reference's
         # per-camera loop (render_final, gaussian_renderer/__init__.py:1217-1288); False keeps the per-camera calls
         self.batched_render = batched_render
