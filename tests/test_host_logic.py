@@ -367,3 +367,43 @@ def test_redistribution_in_one_collective_matches_the_reference_tensor_by_tensor
     assert all(ok for _, ok, _, _, _ in res), res
     assert all(need for _, _, need, _, _ in res)                       # 50 * 1.2 < 87: uneven enough
     assert sum(n for *_, n in res) == sum(50 + 37 * r for r in range(world))
+
+
+def test_device_row_formula_equals_direct_rows():
+    """k_xr_rows (csrc/distribute.cu) computes the destination rows of the direct pack ON THE DEVICE from the all-gathered
+    counts cnt[i][k][j]; its formula, restated here in plain Python, must equal exchange.direct_rows (the host layout the
+    gradient pull and the tensor shapes use) for every rank, and its over-capacity flag the host's decision."""
+    import numpy as np
+    from gs_b200 import exchange
+    rng = np.random.default_rng(3)
+    for W, B in ((2, 1), (2, 2), (4, 3), (8, 8), (16, 5)):
+        cnt = rng.integers(0, 1000, size=(W, B, W)).astype(np.int64)
+        cnt[rng.random(cnt.shape) < 0.2] = 0
+        flat = cnt.reshape(-1)
+        for me in range(W):
+            dev = []
+            for j in range(W):
+                for k in range(B):
+                    r = sum(int(flat[(i * B + kk) * W + j]) for kk in range(k) for i in range(W))
+                    r += sum(int(flat[(i * B + k) * W + j]) for i in range(me))
+                    dev.append(r)
+            row0, view_start = exchange.direct_rows(cnt, me)
+            assert dev == row0
+            assert view_start[-1] == int(cnt[:, :, me].sum())
+        totals = cnt.sum(axis=(0, 1))
+        cap = int(totals.max())
+        assert not any(int(t) > cap for t in totals) and any(int(t) > cap - 1 for t in totals)
+
+
+def test_quantised_buffer_sizes():
+    """ops._q: sizes that follow data-dependent counts are rounded up to at most 1/16 above the count, monotonically, so a
+    slowly varying count maps to few distinct allocation sizes."""
+    from gs_b200 import ops
+    prev = 0
+    for n in list(range(0, 5000, 37)) + [10**5, 10**5 + 1, 5_735_587, 84_000_000, 2**31 - 5]:
+        q = ops._q(n)
+        assert q >= max(n, 1) and q <= max(n, 1) * 1.0626 + 1024
+    xs = sorted(set(ops._q(n) for n in range(5_000_000, 6_000_000, 997)))
+    assert len(xs) <= 8          # a 20 % range of instance counts -> a handful of sizes
+    for a, b in zip(xs, xs[1:]):
+        assert b > a
