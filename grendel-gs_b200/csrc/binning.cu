@@ -104,7 +104,13 @@ k_count_tiles(int P, int W, int H, const float *__restrict__ means2D, const floa
     o[0] = r0; o[1] = r1; o[2] = r2;
 }
 
-// touched counts permuted into depth order (input of the inclusive scan that yields the instance offsets)
+// touched counts in depth order, as an input iterator of the inclusive scan that yields the instance offsets
+struct TouchedInDepthOrder {
+    const uint32_t *order, *touched;
+    __host__ __device__ __forceinline__ uint32_t operator()(int s) const { return touched[order[s]]; }
+};
+
+// touched counts permuted into depth order (kept for callers that want the gathered array)
 __global__ void __launch_bounds__(BIN_THREADS)
 k_gather_touched(int P, const uint32_t *__restrict__ order, const uint32_t *__restrict__ touched,
                  uint32_t *__restrict__ touched_sorted) {
@@ -164,7 +170,12 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static size_t count_cub_bytes(int P) {
     size_t scan = 0, sort = 0;
     const int n = P > 0 ? P : 1;
-    cub::DeviceScan::InclusiveSum(nullptr, scan, (const uint32_t *)nullptr, (uint32_t *)nullptr, n);
+    {
+        cub::CountingInputIterator<int> idx(0);
+        cub::TransformInputIterator<uint32_t, TouchedInDepthOrder, cub::CountingInputIterator<int>> in(
+            idx, TouchedInDepthOrder{nullptr, nullptr});
+        cub::DeviceScan::InclusiveSum(nullptr, scan, in, (uint32_t *)nullptr, n);
+    }
     cub::DeviceRadixSort::SortPairs(nullptr, sort, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 32);
     return align_up(scan > sort ? scan : sort, 256);
@@ -278,9 +289,12 @@ extern "C" int gs_render_count_launch(int num_views, const int32_t *view_start, 
     }
     {
         GsStageTimer timer(GS_STAGE_SCAN, stream);
-        k_gather_touched<<<grid, BIN_THREADS, 0, stream>>>(P, order, touched, touched_sorted);
-        GS_LAUNCH_CHECK();
-        GS_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_temp, cub_bytes, touched_sorted, offsets, P, stream));
+        // the scan reads touched[order[s]] through a transform iterator: no gathered copy, no extra launch
+        (void)touched_sorted;
+        cub::CountingInputIterator<int> idx(0);
+        cub::TransformInputIterator<uint32_t, TouchedInDepthOrder, cub::CountingInputIterator<int>> in(
+            idx, TouchedInDepthOrder{order, touched});
+        GS_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_temp, cub_bytes, in, offsets, P, stream));
     }
     return GS_OK;
 }
