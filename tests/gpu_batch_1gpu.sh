@@ -22,6 +22,10 @@ if [ -n "$NCU" ]; then
   timeout 400 ncu --set full --import-source on --clock-control none -k regex:k_blend -c 2 -f -o $OUT/${TAG}_blend \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_blend.log 2>&1; echo "ncu rc=$?"
 fi
+if [ -n "$LAUNCHES" ]; then   # the ncu launch list of B200_PROFILING.md: per-launch GPU time of every kernel of the bench command
+  timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches_ncu_gputime.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
+fi
 if [ -n "$GAPS" ]; then
   timeout 300 python tests/gap_profile.py --cprofile > $OUT/${TAG}_gaps.log 2>&1; echo "gaps rc=$?"; head -12 $OUT/${TAG}_gaps.log
 fi
