@@ -110,14 +110,6 @@ struct TouchedInDepthOrder {
     __host__ __device__ __forceinline__ uint32_t operator()(int s) const { return touched[order[s]]; }
 };
 
-// touched counts permuted into depth order (kept for callers that want the gathered array)
-__global__ void __launch_bounds__(BIN_THREADS)
-k_gather_touched(int P, const uint32_t *__restrict__ order, const uint32_t *__restrict__ touched,
-                 uint32_t *__restrict__ touched_sorted) {
-    const int s = blockIdx.x * BIN_THREADS + threadIdx.x;
-    if (s < P) touched_sorted[s] = touched[order[s]];
-}
-
 // Stage 40: one (tile, splat id) pair per (splat, local tile), emitted in DEPTH order of the splats.
 __global__ void __launch_bounds__(BIN_THREADS)
 k_duplicate(int P, int W, int H, const float *__restrict__ means2D, const int32_t *__restrict__ radii,
@@ -181,7 +173,7 @@ static size_t count_cub_bytes(int P) {
     return align_up(scan > sort ? scan : sort, 256);
 }
 
-// temp layout: 5 arrays of P uint32 (touched, depth_key, depth_key_sorted, index, touched_sorted) + CUB scratch
+// temp layout: 5 arrays of P uint32 (touched, depth_key, depth_key_sorted, index, one spare) + CUB scratch
 extern "C" size_t gs_render_count_temp_bytes(int P) {
     return 5 * align_up((size_t)(P > 0 ? P : 1) * sizeof(uint32_t), 256) + count_cub_bytes(P) + 256;
 }
@@ -265,7 +257,7 @@ extern "C" int gs_render_count_launch(int num_views, const int32_t *view_start, 
     const size_t stride = align_up((size_t)P * sizeof(uint32_t), 256);
     char *base = (char *)temp;
     uint32_t *touched = (uint32_t *)base, *dkey = (uint32_t *)(base + stride), *dkey_sorted = (uint32_t *)(base + 2 * stride),
-             *index = (uint32_t *)(base + 3 * stride), *touched_sorted = (uint32_t *)(base + 4 * stride);
+             *index = (uint32_t *)(base + 3 * stride);
     void *cub_temp = base + 5 * stride;
     size_t cub_bytes = count_cub_bytes(P);
     unsigned long long *total64 = (unsigned long long *)(base + 5 * stride + cub_bytes);  // the last 256 bytes of temp
@@ -290,7 +282,6 @@ extern "C" int gs_render_count_launch(int num_views, const int32_t *view_start, 
     {
         GsStageTimer timer(GS_STAGE_SCAN, stream);
         // the scan reads touched[order[s]] through a transform iterator: no gathered copy, no extra launch
-        (void)touched_sorted;
         cub::CountingInputIterator<int> idx(0);
         cub::TransformInputIterator<uint32_t, TouchedInDepthOrder, cub::CountingInputIterator<int>> in(
             idx, TouchedInDepthOrder{order, touched});
