@@ -852,6 +852,79 @@ k_xr_pack(XrGeom g, XIn in, const int32_t *__restrict__ blkbase, XrPeers peers, 
     }
 }
 
+// CTA-level compaction (round 2, last step): k_xr_pack lets every WARP store its own hits, and at 8 ranks a warp has ~4
+// hits per destination -- 32-byte means2D spans, 48-byte rgb spans: NVLink write packets far below a cache line.  Here the
+// CTA's hits for one destination (consecutive rows, in thread order: the same rows as k_xr_pack) are staged in shared
+// memory and written by consecutive threads, one row per thread: ~27 rows = 216 / 432 / 324-byte spans per field.
+__global__ void __launch_bounds__(DT_THREADS)
+k_xr_pack_cta(XrGeom g, XIn in, const int32_t *__restrict__ blkbase, XrPeers peers, const int32_t *__restrict__ row0_dev) {
+    __shared__ int32_t s_wcnt[DT_THREADS / 32][XW];
+    __shared__ float2 s_m2[DT_THREADS];
+    __shared__ float4 s_co[DT_THREADS];
+    __shared__ float s_rgb[3 * DT_THREADS];
+    __shared__ int32_t s_rad[DT_THREADS];
+    __shared__ float s_dep[DT_THREADS];
+    __shared__ uint32_t s_any[DT_THREADS / 32];
+    if (row0_dev != nullptr && row0_dev[g.Wr * g.B] != 0) return;   // over capacity: nothing is written (uniform)
+    const int i = blockIdx.x * DT_THREADS + threadIdx.x, k = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool valid = i < g.P;
+    const uint32_t h = xr_hits(g, k, i, valid);
+    const uint32_t wany = __reduce_or_sync(0xffffffffu, h);
+    for (int j = 0; j < g.Wr; j++) {
+        const int c = __popc(__ballot_sync(0xffffffffu, (h >> j) & 1u));
+        if (lane == 0) s_wcnt[warp][j] = c;
+    }
+    if (lane == 0) s_any[warp] = wany;
+    __syncthreads();
+    uint32_t any = 0u;
+#pragma unroll
+    for (int w = 0; w < DT_THREADS / 32; w++) any |= s_any[w];
+    if (any == 0u) return;
+    float2 m = make_float2(0.f, 0.f);
+    float4 co = make_float4(0.f, 0.f, 0.f, 0.f);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, dep = 0.f;
+    int rad = 0;
+    if (h) {
+        m = *reinterpret_cast<const float2 *>(in.m2[k] + 2 * (size_t)i);
+        co = *reinterpret_cast<const float4 *>(in.co[k] + 4 * (size_t)i);
+        r0 = in.rgb[k][3 * (size_t)i]; r1 = in.rgb[k][3 * (size_t)i + 1]; r2 = in.rgb[k][3 * (size_t)i + 2];
+        rad = in.rad[k][i]; dep = in.dep[k][i];
+    }
+    const long long cap = peers.cap;
+    while (any) {
+        const int j = __ffs(any) - 1;
+        any &= any - 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, (h >> j) & 1u);
+        int lr = __popc(bal & ((1u << lane) - 1u)), cnt = 0;
+#pragma unroll
+        for (int w = 0; w < DT_THREADS / 32; w++) {
+            const int c = s_wcnt[w][j];
+            if (w < warp) lr += c;
+            cnt += c;
+        }
+        if ((h >> j) & 1u) {   // rank lr among the CTA's hits for destination j = its row offset
+            s_m2[lr] = m; s_co[lr] = co; s_rad[lr] = rad; s_dep[lr] = dep;
+            s_rgb[3 * lr] = r0; s_rgb[3 * lr + 1] = r1; s_rgb[3 * lr + 2] = r2;
+        }
+        __syncthreads();
+        const size_t col = (size_t)j * g.B + k;
+        const long long row = (long long)(row0_dev ? row0_dev[col] : peers.row0[col]) +
+                              (blkbase[col * gridDim.x + blockIdx.x] - blkbase[col * gridDim.x]);   // the CTA's first row
+        float *b = reinterpret_cast<float *>(peers.base[j]);
+        const int t = threadIdx.x;
+        if (t < cnt) {
+            reinterpret_cast<float2 *>(b + 2 * row)[t] = s_m2[t];
+            reinterpret_cast<float4 *>(b + 5 * cap + 4 * row)[t] = s_co[t];
+            reinterpret_cast<int32_t *>(b + 9 * cap)[row + t] = s_rad[t];
+            (b + 10 * cap)[row + t] = s_dep[t];
+        }
+        float *q = b + 2 * cap + 3 * row;
+        for (int u = t; u < 3 * cnt; u += DT_THREADS) q[u] = s_rgb[u];
+        __syncthreads();   // the staging arrays are reused for the next destination
+    }
+}
+
 __global__ void __launch_bounds__(DT_THREADS)
 k_xr_pull_grad(XrGeom g, const int32_t *__restrict__ blkbase, XrPeers peers, XOut out) {
     __shared__ int32_t s_wcnt[DT_THREADS / 32][XW];
@@ -969,7 +1042,10 @@ extern "C" int gs_xr_pack(int B, int P, int W, int image_height, int image_width
     XIn in;
     fill_in(in, B, means2D_ptrs_host, rgb_ptrs_host, conic_opacity_ptrs_host, radii_ptrs_host, depths_ptrs_host);
     GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
-    k_xr_pack<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers, nullptr);
+    if (g_gs_debug_flags & GS_DEBUG_XR_PACK_CTA)
+        k_xr_pack_cta<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers, nullptr);
+    else
+        k_xr_pack<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers, nullptr);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
@@ -1000,7 +1076,10 @@ extern "C" int gs_xr_pack_dev(int B, int P, int W, int image_height, int image_w
     XIn in;
     fill_in(in, B, means2D_ptrs_host, rgb_ptrs_host, conic_opacity_ptrs_host, radii_ptrs_host, depths_ptrs_host);
     GsStageTimer timer(GS_STAGE_PACK, (cudaStream_t)stream);
-    k_xr_pack<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers, row0_dev);
+    if (g_gs_debug_flags & GS_DEBUG_XR_PACK_CTA)
+        k_xr_pack_cta<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers, row0_dev);
+    else
+        k_xr_pack<<<dim3(XR_NB(P), B), DT_THREADS, 0, (cudaStream_t)stream>>>(g, in, blkbase, peers, row0_dev);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

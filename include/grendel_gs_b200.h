@@ -270,7 +270,10 @@ enum {
     GS_DEBUG_BWD_TILE = 2,
     /* gs_render_forward: the half-warp-per-4x4-block blend kernel of round 1 (k_blend_fwd) instead of the packed
      * two-pixels-per-lane kernel (k_blend_fwd2); the images are bit-identical. */
-    GS_DEBUG_FWD_HALFWARP = 4
+    GS_DEBUG_FWD_HALFWARP = 4,
+    /* direct exchange: pack with a CTA-level compaction per destination (one row per thread, 200-400-byte NVLink spans)
+     * instead of per-warp stores; same rows, same bytes (A/B switch until it is measured at 8 ranks) */
+    GS_DEBUG_XR_PACK_CTA = 8
 };
 GS_API int gs_debug_set(int flags);
 

@@ -278,6 +278,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    flags = int(os.environ.get("GS_B200_DEBUG_FLAGS", "0"))   # A/B switches of the library (include/grendel_gs_b200.h)
+    if flags:
+        from gs_b200 import _lib
+        _lib.debug_set(flags)
+        if rank == 0:
+            print(f"[mgpu] GS_B200_DEBUG_FLAGS = {flags}", flush=True)
     summary = check(dev, rank, world, verbose=True)
     ok = torch.tensor([1.0 if (rank != 0 or summary.get("ok")) else 0.0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
