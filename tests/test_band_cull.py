@@ -149,3 +149,25 @@ def test_band_cull_is_conservative(name):
     assert t["kept"] <= t["box"]
     if name in ("ordinary", "anisotropic"):
         assert t["kept"] < 0.9 * t["box"]   # it has to pay for itself
+
+
+def test_unsigned_compare_is_the_range_test():
+    """The blend kernels test `thr <= power <= 0` as ONE unsigned compare of bit patterns on q = -power, t = -thr >= 0
+    (csrc/blend.cu, staging of k_blend_fwd2 / k_blend_bwd_seg): for every fp32 q -- positive, negative, +-0, subnormal, inf,
+    NaN of either sign -- `bits(q) <= bits(t)` must equal `0 <= q <= t`, except q = -0.0, which the kernels cannot produce
+    (the non-negative gamma' dy^2 is added last: x + (+0) is never -0)."""
+    rng = np.random.default_rng(0)
+    special = np.array([0.0, np.finfo(F).tiny, 1e-45, 1.0, 5.54, 88.0, 3e38, np.inf, np.nan, -np.nan,
+                        -1e-45, -np.finfo(F).tiny, -1.0, -3e38, -np.inf], dtype=F)
+    q = np.concatenate([special, rng.normal(0, 10, 20000).astype(F), rng.uniform(0, 12, 20000).astype(F),
+                        rng.integers(0, 2**32, 20000, dtype=np.uint64).astype(np.uint32).view(F)])
+    q = q[q.view(np.uint32) != 0x80000000]          # -0.0: excluded by construction in the kernels
+    for t in (F(0.0), F(1e-3), F(0.5), F(5.5412), F(87.3)):
+        with np.errstate(invalid="ignore"):
+            want = (q >= 0) & (q <= t)
+        got = q.view(np.uint32) <= np.array(t, dtype=F).view(np.uint32)
+        assert np.array_equal(want, got), t
+    # and the sum that produces q never yields -0: (anything) + (+0 or positive) under round-to-nearest
+    a = np.array([-0.0, 0.0, -1e-45, 1e-45], dtype=F)
+    for b in (F(0.0), F(1e-45), F(2.0)):
+        assert not np.any((a + b).view(np.uint32) == 0x80000000)
