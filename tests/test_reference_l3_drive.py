@@ -3,7 +3,8 @@
 
 `distributed_preprocess3dgs_and_all2all_final` -> `render_final` -> `batched_loss_computation` -> `loss.backward()` ->
 `finish_strategy_final` (/root/reference/gaussian_renderer/__init__.py:878-1037, 1217-1288; loss_distribution.py:2536-2637;
-workload_division.py:944-998; train_internal.py:139-196) run UNMODIFIED on CPU tensors with W = 1, a real reference
+workload_division.py:944-998; train_internal.py:139-196) -- and then the LEGACY sequence `replicated_preprocess3dgs` ->
+`render` with a flat `DivisionStrategy` and its `extended_compute_locally` mask (:66-174, :458-507) -- run UNMODIFIED on CPU tensors with W = 1, a real reference
 `GaussianModel` holding the parameters and a real `DivisionStrategyFinal`.  There is no GPU here, so the two operator
 methods of OUR `diff_gaussian_rasterization.GaussianRasterizer` are replaced by recorders that (a) assert every argument
 the reference passes (keyword names, dtypes, shapes, the 12 settings fields, the cuda_args keys) against the contract of
@@ -216,6 +217,58 @@ for name, r in raw.items():
     err = np.abs(g - r)
     assert (err <= 2e-4 * np.abs(r) + 2e-4 * rms).mean() > 0.999, (name, err.max(), rms)
 print("L3-DRIVE-OK loss", got)
+
+# ---- the LEGACY single-camera sequence (gaussian_renderer/__init__.py:66-174 replicated_preprocess3dgs, :458-507 render;
+#      workload_division.py:100-199 DivisionStrategy): flat tile-range division, dist_global_strategy in cuda_args, and an
+#      extended_compute_locally mask (the local tile range dilated by one tile row + 1) handed to render_gaussians -------
+from gaussian_renderer.distribution_config import ImageDistributionConfig
+args.image_distribution_config = ImageDistributionConfig("replicated_loss_computation", "DivisionStrategyUniform", False,
+                                                         ["backward_render_time"])
+for t in (pc._xyz, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation, pc._opacity):
+    t.grad = None
+LEGACY = {"on": True, "ext": None, "cl": None}
+CUDA_ARGS_KEYS.add("dist_global_strategy")
+_orig_render = render_gaussians
+def render_gaussians_legacy(self, *pos, **kw):
+    ext, cl = kw["extended_compute_locally"], kw["compute_locally"]
+    assert ext is not None and ext.dtype == torch.bool and tuple(ext.shape) == (utils.TILE_Y, utils.TILE_X)
+    assert bool((ext | ~cl).all())                                           # the dilated region covers the local one
+    assert isinstance(kw["cuda_args"]["dist_global_strategy"], str)
+    LEGACY["ext"], LEGACY["cl"] = ext, cl
+    # the drop-in's own argument validation of the legacy mask (gs_b200.ops.render_gaussians) on exactly these arguments:
+    # a covering mask gets as far as the device check ("no CPU path"), a mask that does not cover compute_locally is rejected
+    from gs_b200 import ops
+    a = (kw["means2D"].detach(), kw["conic_opacity"].detach(), kw["rgb"].detach(), kw["depths"], kw["radii"], cl, self.raster_settings)
+    try:
+        ops.render_gaussians(*a, kw["cuda_args"], extended_compute_locally=ext)
+        raise AssertionError("CPU tensors must not pass")
+    except ValueError as e:
+        assert "CUDA tensor" in str(e), e
+    try:
+        ops.render_gaussians(*a, kw["cuda_args"], extended_compute_locally=torch.zeros_like(ext))
+        raise AssertionError("a mask that does not cover compute_locally must be rejected")
+    except ValueError as e:
+        assert "cover" in str(e), e
+    kw = dict(kw, extended_compute_locally=None)
+    return _orig_render(self, **kw)
+dgr.GaussianRasterizer.render_gaussians = render_gaussians_legacy
+calls.clear()
+legacy_strategy = wd.DivisionStrategy(camera, 1, 0, utils.TILE_X, utils.TILE_Y,
+                                      torch.ones((utils.TILE_Y, utils.TILE_X)), "DivisionStrategyUniform")
+pkg1 = gr.replicated_preprocess3dgs(camera, pc, pipe, bg, strategy=legacy_strategy, mode="train")
+img1, cl1 = gr.render(pkg1, legacy_strategy)
+assert calls == ["preprocess", "render"], calls
+assert LEGACY["ext"] is not None and bool(LEGACY["ext"].all()) and bool(cl1.all())    # W = 1: everything is local
+assert torch.allclose(img1, torch.tensor(ref["fwd"]["image"]), atol=2e-6), float((img1 - torch.tensor(ref["fwd"]["image"])).abs().max())
+wgt = torch.tensor(np.random.default_rng(2).normal(size=(3, H, W)).astype(np.float32))
+(img1 * wgt).sum().backward()
+assert pkg1["locally_preprocessed_mean2D"].grad is not None and pc._xyz.grad is not None
+rb = orc.render_backward(H, W, ref["pre"]["means2D"], ref["pre"]["conic_opacity"], ref["pre"]["rgb"], (0.0, 0.0, 0.0),
+                         ref["fwd"], wgt.numpy())
+g2 = pkg1["locally_preprocessed_mean2D"].grad.numpy()
+rms = float(np.sqrt((rb["means2D"].astype(np.float64) ** 2).mean()))
+assert (np.abs(g2 - rb["means2D"]) <= 2e-4 * np.abs(rb["means2D"]) + 2e-4 * rms).mean() > 0.999
+print("L3-LEGACY-OK")
 '''
 
 
@@ -224,4 +277,4 @@ def test_reference_step_functions_run_over_the_dropin_boundary():
                        ref=REF, root=ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd="/tmp")
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
-    assert "L3-DRIVE-OK" in r.stdout
+    assert "L3-DRIVE-OK" in r.stdout and "L3-LEGACY-OK" in r.stdout
