@@ -128,7 +128,7 @@ def gather_counts(local_counts, group=None):
     flat = local_counts.contiguous().reshape(-1)
     allc = torch.empty((W * flat.numel(),), dtype=flat.dtype, device=flat.device)
     dist.all_gather_into_tensor(allc, flat, group=group)
-    allp = _piggyback_gather(flat.device, W, group) if flat.is_cuda else None
+    allp = _piggyback_gather(flat.device, W, group)
     out = allc.reshape((W,) + tuple(local_counts.shape)).cpu().numpy()
     PIGGYBACK_OUT = None if allp is None else allp.reshape(W, -1).cpu().numpy()
     return out
